@@ -1,0 +1,140 @@
+"""ctypes front-end to the two CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+  * ``port()``  -> oracle/libtrc_oracle.so, our scalar C restatement (symbols ``orc_<name>``)
+  * ``ref()``   -> oracle/_ref/libtrcref.so, the unmodified reference compiled by oracle/Makefile
+                   (symbols carry the reference's own names); None when it was never built.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
+module.  Nothing under turbo-range-coder_b200/ does.
+
+Both objects expose the same two calls so tests can run either through the same code:
+    enc(name, data, cdf=None, cdfnum=None) -> (returned length, bytes written (out[:len]))
+    dec(name, stream, outlen, cdf=None, cdfnum=None) -> decoded bytes
+Buffers are laid out ``[in | pad | out]`` in ONE allocation so that ``out`` lies above ``in``: the
+reference's anscdf4senc compares its output cursor with the input pointer (anscdf.c:63,66) and returns
+a raw copy whenever ``out < in``.
+"""
+import ctypes
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+# name -> (kind, needs_cdf, needs_cdfnum)
+ENCODERS = {
+    "anscdf4senc": (True, False), "anscdf4enc": (False, False), "anscdfenc": (False, False),
+    "anscdf1enc": (False, False), "rccdfsenc": (True, True), "rccdfs2enc": (True, True),
+    "rccdfenc": (False, False), "rccdfienc": (False, False), "rccdf4enc": (False, False),
+    "rccdf4ienc": (False, False),
+}
+DECODERS = {
+    "anscdf4sdec": (True, False), "anscdf4dec": (False, False), "anscdfdec": (False, False),
+    "anscdf1dec": (False, False), "rccdfsbdec": (True, True), "rccdfsb2dec": (True, True),
+    "rccdfsldec": (True, True), "rccdfsl2dec": (True, True),
+    "rccdfdec": (False, False), "rccdfidec": (False, False), "rccdf4dec": (False, False),
+    "rccdf4idec": (False, False),
+    # port-only (no reference counterpart): true inverses with the tail state fixed / wide alphabet
+    "ans_sdec_n": (True, True), "anscdf4dec_fix": (False, False),
+}
+PAIRS = {  # encoder -> decoder the reference harness pairs it with (turborc.c:495-536)
+    "anscdf4senc": "anscdf4sdec", "anscdf4enc": "anscdf4dec", "anscdfenc": "anscdfdec",
+    "anscdf1enc": "anscdf1dec", "rccdfsenc": "rccdfsbdec", "rccdfs2enc": "rccdfsb2dec",
+    "rccdfenc": "rccdfdec", "rccdfienc": "rccdfidec", "rccdf4enc": "rccdf4dec",
+    "rccdf4ienc": "rccdf4idec",
+}
+
+
+class _Lib:
+    def __init__(self, path, prefix):
+        self.lib = ctypes.CDLL(path)
+        self.prefix = prefix
+        self.path = path
+
+    def _fn(self, name, restype=ctypes.c_size_t):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype = restype
+        return f
+
+    def has(self, name):
+        return hasattr(self.lib, self.prefix + name)
+
+    def cdfini(self, data, cdfnum=256):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        cdf = np.zeros(257, np.uint16)
+        r = self._fn("cdfini", ctypes.c_int)(ctypes.c_void_p(data.ctypes.data), ctypes.c_size_t(data.size),
+                                              ctypes.c_void_p(cdf.ctypes.data), ctypes.c_uint(cdfnum))
+        if r < 0:
+            raise ValueError("cdfini: degenerate distribution")
+        return cdf
+
+    @staticmethod
+    def _extra(needs, cdf, cdfnum, keep):
+        args = []
+        if needs[0]:
+            c = np.ascontiguousarray(cdf, dtype=np.uint16)
+            keep.append(c)
+            args.append(ctypes.c_void_p(c.ctypes.data))
+        if needs[1]:
+            args.append(ctypes.c_uint(int(cdfnum)))
+        return args
+
+    def enc(self, name, data, cdf=None, cdfnum=None):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        n = data.size
+        cap = n + n // 2 + 4096
+        buf = np.zeros(n + 64 + cap, np.uint8)
+        buf[:n] = data
+        keep = []
+        args = self._extra(ENCODERS[name], cdf, cdfnum, keep)
+        pin = buf.ctypes.data
+        pout = pin + n + 64
+        r = self._fn(name)(ctypes.c_void_p(pin), ctypes.c_size_t(n), ctypes.c_void_p(pout), *args)
+        m = min(int(r), n) if r <= cap else 0
+        return int(r), buf[n + 64: n + 64 + max(m, 0)].copy()
+
+    def dec(self, name, stream, outlen, cdf=None, cdfnum=None):
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        buf = np.zeros(stream.size + 64 + outlen + 64, np.uint8)     # decoders over-read <= 4 B
+        buf[:stream.size] = stream
+        keep = []
+        args = self._extra(DECODERS[name], cdf, cdfnum, keep)
+        pin = buf.ctypes.data
+        pout = pin + stream.size + 64
+        self._fn(name)(ctypes.c_void_p(pin), ctypes.c_size_t(outlen), ctypes.c_void_p(pout), *args)
+        return buf[stream.size + 64: stream.size + 64 + outlen].copy()
+
+    def raw_fn(self, name):
+        """Bare ctypes function (for timing loops that manage their own buffers)."""
+        return self._fn(name)
+
+
+def build(ref_too=True):
+    """(Re)build the checkers with oracle/Makefile.  Building the checker is not using it."""
+    subprocess.run(["make", "-s", "-C", _HERE, "port"], check=True)
+    if ref_too:
+        subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+
+
+_port = _ref = None
+
+
+def port():
+    global _port
+    if _port is None:
+        p = os.path.join(_HERE, "libtrc_oracle.so")
+        if not os.path.exists(p):
+            build(ref_too=False)
+        _port = _Lib(p, "orc_")
+    return _port
+
+
+def ref():
+    """The compiled reference, or None if oracle/_ref/libtrcref.so was never built."""
+    global _ref
+    if _ref is None:
+        p = os.path.join(_HERE, "_ref", "libtrcref.so")
+        if not os.path.exists(p):
+            return None
+        _ref = _Lib(p, "")
+    return _ref
