@@ -1,0 +1,208 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the golden vectors.
+
+Everything here is bit-exact integer/byte work: compressed bytes, lengths, offsets and decoded bytes must be
+identical to the reference semantics (oracle per chunk == one reference call per chunk)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import CODECS, chunks, cpu_batch, first_diff
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+
+
+def _tabs(port, codec, d):
+    need_cdf = CODECS[codec][2]
+    if not need_cdf:
+        return None, 0
+    return port.cdfini(d), int(d.max()) + 1
+
+
+def _check_batch(trc, port, codec, d, chunk_len, label):
+    enc, dec, need_cdf, nib = CODECS[codec]
+    cdf, num = _tabs(port, codec, d)
+    want, woff = cpu_batch(port, codec, d, chunk_len, cdf, num)
+    got, goff = trc.enc_batch_host(codec, d, chunk_len, cdf=cdf, cdfnum=num)
+    assert np.array_equal(goff, woff), (label, enc, chunk_len, "offsets", first_diff(goff, woff))
+    assert np.array_equal(got, want), (label, enc, chunk_len, "bytes differ at", first_diff(got, want))
+    # decode what we produced
+    quirk = any(int(woff[c + 1] - woff[c]) < l and np.array_equal(want[int(woff[c]):int(woff[c + 1])], d[s:s + int(woff[c + 1] - woff[c])])
+                for c, (s, l) in enumerate(chunks(d.size, chunk_len)))
+    if quirk:                                   # rccdf4ienc raw-with-short-length: not decodable, by the reference either
+        return
+    back = trc.dec_batch_host(codec, got, goff, d.size, chunk_len, cdf=cdf, cdfnum=num)
+    assert np.array_equal(back, d), (label, dec, chunk_len, "round trip differs at", first_diff(back, d))
+    if codec in (0, 1):                          # reference-compatible tail handling == oracle's faithful decoders
+        back = trc.dec_batch_host(codec, got, goff, d.size, chunk_len, cdf=cdf, cdfnum=num, flags=trc.F_REF_TAIL)
+        for c, (s, l) in enumerate(chunks(d.size, chunk_len)):
+            a, b = int(goff[c]), int(goff[c + 1])
+            if b - a == l:
+                assert np.array_equal(back[s:s + l], d[s:s + l])
+            else:
+                exp = port.dec(dec, got[a:b], l, cdf, num)
+                assert np.array_equal(back[s:s + l], exp), (label, dec, "ref tail", c)
+
+
+@pytest.mark.parametrize("codec", sorted(CODECS))
+def test_batch_parity_small(trc, port, sources, dg, codec):
+    """Ragged and tiny geometries: tails of 1-3 bytes, odd lengths, chunks that hit the raw-copy rules."""
+    nib = CODECS[codec][3]
+    for sname, src in sources.items():
+        for n, chunk_len in [(8, 8), (100, 33), (1001, 1001), (1003, 250), (4099, 1000), (20000, 4096), (65537, 65537), (70001, 16384)]:
+            d = src[:n]
+            if nib:
+                d = dg.nibbles(d)
+            _check_batch(trc, port, codec, d, chunk_len, f"{sname}/{n}")
+
+
+@pytest.mark.parametrize("codec", sorted(CODECS))
+def test_batch_parity_300k(trc, port, sources, dg, codec):
+    nib = CODECS[codec][3]
+    for sname in ("zipf", "bwt"):
+        d = sources[sname]
+        if nib:
+            d = dg.nibbles(d)
+        for chunk_len in (4096, 65536):
+            _check_batch(trc, port, codec, d, chunk_len, sname)
+
+
+@pytest.mark.parametrize("codec", sorted(CODECS))
+def test_golden_vectors(trc, dg, codec):
+    """Bytes produced by the compiled reference itself (tests/golden/make_golden.py)."""
+    enc, dec, need_cdf, nib = CODECS[codec]
+    for key in sorted(k for k in G.files if k.startswith("in/")):
+        _, sname, n = key.split("/")
+        d = G[key]
+        x = dg.nibbles(d) if nib else d
+        cdf = (G[f"cdfn/{sname}/{n}"] if nib else G[f"cdf/{sname}/{n}"]) if need_cdf else None
+        num = int(x.max()) + 1 if need_cdf else 0
+        got, off = trc.enc_batch_host(codec, x, x.size, cdf=cdf, cdfnum=num)
+        assert int(off[1]) == int(G[f"len/{enc}/{sname}/{n}"][0]), (enc, key)
+        assert np.array_equal(got, G[f"enc/{enc}/{sname}/{n}"]), (enc, key)
+        dk = f"dec/{dec}/{sname}/{n}"
+        if dk in G.files:
+            back = trc.dec_batch_host(codec, got, off, x.size, x.size, cdf=cdf, cdfnum=num, flags=trc.F_REF_TAIL)
+            assert np.array_equal(back, G[dk]), (dec, key)
+
+
+def test_static_rans_byte_alphabet(trc, port, dg):
+    """256-symbol static rANS: encoder bit-exact with the reference's anscdf4senc run on bytes, decoder inverts it."""
+    for key in sorted(k for k in G.files if k.startswith("enc/anscdf4senc.bytes/")):
+        _, _, sname, n = key.split("/")
+        d, cdf = G[f"in/{sname}/{n}"], G[f"cdf/{sname}/{n}"]
+        got, off = trc.enc_batch_host(trc.ANS4S, d, d.size, cdf=cdf, cdfnum=256)
+        assert np.array_equal(got, G[key]), key
+        assert np.array_equal(trc.dec_batch_host(trc.ANS4S, got, off, d.size, d.size, cdf=cdf, cdfnum=256), d)
+    d = dg.zipf(1_000_003)
+    cdf = port.cdfini(d)
+    for chunk_len in (4096, 100_000):
+        want, woff = cpu_batch(port, trc.ANS4S, d, chunk_len, cdf, 256)
+        got, goff = trc.enc_batch_host(trc.ANS4S, d, chunk_len, cdf=cdf, cdfnum=256)
+        assert np.array_equal(goff, woff) and np.array_equal(got, want)
+        assert np.array_equal(trc.dec_batch_host(trc.ANS4S, got, goff, d.size, chunk_len, cdf=cdf, cdfnum=256), d)
+
+
+def test_uniform_is_raw(trc, dg):
+    """BASELINE config 1: 1 MiB uniform bytes through -e45 (rccdfs2enc) is a raw copy, l == n."""
+    d = dg.uniform(1 << 20)
+    cdf = trc.cdfini(d)
+    l, out = trc.dropin_enc("rccdfs2enc", d, cdf, 256)
+    assert l == d.size and np.array_equal(out, d)
+    got, off = trc.enc_batch_host(trc.RCS2, d, 65536, cdf=cdf, cdfnum=256)
+    assert int(off[-1]) == d.size and np.array_equal(got, d)
+    assert np.array_equal(trc.dec_batch_host(trc.RCS2, got, off, d.size, 65536, cdf=cdf, cdfnum=256), d)
+
+
+def test_cdfini(trc, port, sources, dg):
+    for sname, src in sources.items():
+        for n in (1, 7, 1000, 300000):
+            d = src[:n]
+            assert np.array_equal(trc.cdfini(d), port.cdfini(d)), (sname, n)
+            dn = dg.nibbles(d)
+            assert np.array_equal(trc.cdfini(dn), port.cdfini(dn)), (sname, n)
+
+
+def test_per_block_tables(trc, port, dg):
+    """One cdfini table per group of chunks (BASELINE config 5 shape: table per 64 MB block of small chunks)."""
+    import torch
+    d = dg.zipf(200_000)
+    d[100_000:] = dg.bwt_shaped(100_000)
+    chunk_len, cpc = 4096, 8
+    nt = -(-trc.num_chunks(d.size, chunk_len) // cpc)
+    t = torch.from_numpy(d).cuda()
+    cdf_dev, status = trc.cdfini_dev(t, d.size, chunk_len * cpc)
+    assert int(status.abs().sum().item()) == 0
+    cdf = cdf_dev.cpu().numpy().view(np.uint16).reshape(nt, 257)
+    for k in range(nt):
+        assert np.array_equal(cdf[k], port.cdfini(d[k * chunk_len * cpc:(k + 1) * chunk_len * cpc]))
+    for codec in (trc.ANS4S, trc.RCS, trc.RCS2):
+        want, woff = cpu_batch(port, codec, d, chunk_len, cdf, 256, cpc)
+        got, goff = trc.enc_batch_host(codec, d, chunk_len, cdf=cdf, cdfnum=256, chunks_per_cdf=cpc)
+        assert np.array_equal(goff, woff) and np.array_equal(got, want), codec
+        back = trc.dec_batch_host(codec, got, goff, d.size, chunk_len, cdf=cdf, cdfnum=256, chunks_per_cdf=cpc)
+        assert np.array_equal(back, d), codec
+    # groups that do not align with the CTA size exercise the per-thread global-table path
+    for codec in (trc.ANS4S, trc.RCS2):
+        cpc2 = 3
+        nt2 = -(-trc.num_chunks(d.size, chunk_len) // cpc2)
+        cdf2 = np.stack([port.cdfini(d[k * chunk_len * cpc2:(k + 1) * chunk_len * cpc2]) for k in range(nt2)])
+        want, woff = cpu_batch(port, codec, d, chunk_len, cdf2, 256, cpc2)
+        got, goff = trc.enc_batch_host(codec, d, chunk_len, cdf=cdf2, cdfnum=256, chunks_per_cdf=cpc2)
+        assert np.array_equal(goff, woff) and np.array_equal(got, want), codec
+        assert np.array_equal(trc.dec_batch_host(codec, got, goff, d.size, chunk_len, cdf=cdf2, cdfnum=256, chunks_per_cdf=cpc2), d)
+
+
+def test_dropin_symbols(trc, port, dg):
+    """The reference-named whole-buffer entry points (host pointers), as the turborc harness calls them."""
+    d = dg.bwt_shaped(50_001)
+    dn = dg.nibbles(d)
+    cdf, cdfn = trc.cdfini(d), trc.cdfini(dn)
+    assert np.array_equal(cdf, port.cdfini(d))
+    for codec, (enc, dec, need_cdf, nib) in CODECS.items():
+        x = dn if nib else d
+        tab = (cdfn if nib else cdf) if need_cdf else None
+        num = (int(x.max()) + 1) if need_cdf else None
+        l, s = trc.dropin_enc(enc, x, tab, num)
+        lw, sw = port.enc(enc, x, tab, num)
+        assert l == lw and np.array_equal(s, sw), enc
+        if l < x.size:
+            back = trc.dropin_dec(dec, s, x.size, tab, num)
+            assert np.array_equal(back, port.dec(dec, sw, x.size, tab, num)), dec
+    # the per-ISA aliases the harness names (turborc.c:516-521) resolve to the same path
+    l, s = trc.dropin_enc("anscdfencx", d)
+    assert (l, s.tobytes()) == (lambda r: (r[0], r[1].tobytes()))(port.enc("anscdfenc", d))
+    assert np.array_equal(trc.dropin_dec("anscdfdecs", s, d.size), d)
+
+
+def test_multiblock_whole_call(trc, port, dg):
+    """inlen > 4 MiB: blocks are coded independently and concatenated; order-1 carries cx across blocks;
+    the decoder walks the blocks sequentially (no block directory in the format)."""
+    d = dg.zipf((1 << 22) + 4097)
+    for codec in (trc.ANS, trc.ANS1):
+        enc, dec = CODECS[codec][0], CODECS[codec][1]
+        want = port.enc(enc, d)
+        got, off = trc.enc_batch_host(codec, d, d.size)
+        assert int(off[1]) == want[0] and np.array_equal(got, want[1]), enc
+        assert np.array_equal(trc.dec_batch_host(codec, got, off, d.size, d.size), d), dec
+
+
+def test_device_api_matches_host_api(trc, port, dg):
+    import torch
+    d = dg.zipf(1_000_000)
+    cdf = port.cdfini(d)
+    for codec in (trc.ANS4S, trc.RCS2, trc.ANS, trc.RC):
+        b = trc.DeviceBatch(codec, d.size, 4096, cdfnum=256 if codec in trc.STATIC else 0)
+        if codec in trc.STATIC:
+            b.set_cdf(cdf)
+        t = torch.from_numpy(d).cuda()
+        b.encode(t)
+        torch.cuda.synchronize()
+        n = b.compressed_len()
+        got = b.out[:n].cpu().numpy()
+        off = b.off.cpu().numpy().astype(np.uint64)
+        want, woff = trc.enc_batch_host(codec, d, 4096, cdf=cdf if codec in trc.STATIC else None, cdfnum=256 if codec in trc.STATIC else 0)
+        assert np.array_equal(off, woff) and np.array_equal(got, want)
+        back = b.decode().cpu().numpy()
+        assert np.array_equal(back, d)

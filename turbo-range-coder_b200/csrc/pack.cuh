@@ -1,0 +1,161 @@
+// pack.cuh -- everything around the coders: per-call length/raw resolution + prefix sum (k_resolve_scan),
+// the layout pass that writes each call's bytes exactly where and how the reference does (k_pack), and the
+// static-table builder cdfini (rccdf.c:50-68) as histogram + normalise kernels.
+#pragma once
+#include "trc_common.cuh"
+
+namespace trc {
+
+struct CallInfo { uint32_t len; uint32_t raw; };   // raw: 0 coded, 1 raw copy of `len` input bytes
+
+// ---- resolve + scan ------------------------------------------------------------------------------------
+// Per call: combine its units.  For the blocked rANS codecs this applies the mnflush guards
+// (anscdf_.h:131-136) which depend on where the block lands in the call's output: with o = bytes of the
+// previous blocks, L = bytes of this block, N = inlen of the call, the reference bails out to a raw copy iff
+//     o + L + (the last-coded record emitted a word ? 0 : 2)  >=  N
+// (DESIGN.md derives this from the per-record guard `ep <= op + 2 + 4n` and the two post-checks).
+// Then an exclusive prefix sum over the call lengths gives the packed offsets.  Single CTA.
+constexpr int SCAN_NT = 1024;
+
+__global__ void __launch_bounds__(SCAN_NT)
+k_resolve_scan(Geom g, int blocked, UnitMeta *__restrict__ meta, CallInfo *__restrict__ calls, uint64_t *__restrict__ out_off) {
+    __shared__ uint64_t part[SCAN_NT];
+    const size_t per = (g.n_calls + SCAN_NT - 1) / SCAN_NT;
+    const size_t j0 = (size_t)threadIdx.x * per, j1 = j0 + per < g.n_calls ? j0 + per : g.n_calls;
+    uint64_t sum = 0;
+    for (size_t j = j0; j < j1; j++) {
+        size_t cs, N; call_span(g, j, cs, N);
+        CallInfo ci;
+        if (blocked) {
+            uint64_t o = 0; bool raw = false;
+            for (uint32_t b = 0; b < g.upc; b++) {
+                UnitMeta &m = meta[j * g.upc + b];
+                if (m.a_len == 0 && m.len == 0) break;                 // padding unit of a short last call
+                if ((m.flags & UM_OVF) || o + m.len + ((m.flags & UM_ADJ2) ? 2 : 0) >= N) { raw = true; break; }
+                m.pref = (uint32_t)o; o += m.len;
+            }
+            ci.raw = raw; ci.len = raw ? (uint32_t)N : (uint32_t)o;
+        } else {
+            const UnitMeta &m = meta[j];
+            ci.raw = (m.flags & UM_RAW) ? 1 : 0; ci.len = m.len;
+        }
+        calls[j] = ci; sum += ci.len;
+    }
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < SCAN_NT; d <<= 1) {                            // Hillis-Steele inclusive scan of the partials
+        uint64_t v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint64_t run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+    for (size_t j = j0; j < j1; j++) { out_off[j] = run; run += calls[j].len; }
+    if (threadIdx.x == SCAN_NT - 1) out_off[g.n_calls] = part[SCAN_NT - 1];
+}
+
+// ---- pack ----------------------------------------------------------------------------------------------
+// grid = (n_units, segments); each CTA moves one `seg`-byte segment of one unit's output.
+constexpr int    PACK_NT  = 128;
+constexpr size_t PACK_SEG_MIN = 16384;
+
+__global__ void __launch_bounds__(PACK_NT)
+k_pack(const uint8_t *__restrict__ in, Geom g, const uint8_t *__restrict__ slots, size_t slot_stride,
+       const UnitMeta *__restrict__ meta, const CallInfo *__restrict__ calls, const uint64_t *__restrict__ out_off,
+       uint8_t *__restrict__ out, size_t PACK_SEG) {
+    const size_t u = blockIdx.x;
+    size_t j, start, len; uint32_t b;
+    unit_span(g, u, j, b, start, len);
+    if (len == 0) return;
+    const CallInfo ci = calls[j];
+    const size_t seg0 = (size_t)blockIdx.y * PACK_SEG;
+    if (ci.raw) {                                                       // raw copy of (a prefix of) the call's input
+        size_t cs = j * g.chunk, uo = start - cs;                      // this unit's share of the call
+        if (uo >= ci.len) return;
+        size_t n = ci.len - uo < len ? ci.len - uo : len;
+        if (seg0 >= n) return;
+        size_t m = n - seg0 < PACK_SEG ? n - seg0 : PACK_SEG;
+        group_copy(out + out_off[j] + uo + seg0, in + start + seg0, m, threadIdx.x, PACK_NT);
+        return;
+    }
+    const UnitMeta m = meta[u];
+    const size_t total = (size_t)m.a_len + m.b_len;
+    if (seg0 >= total) return;
+    size_t seg1 = seg0 + PACK_SEG < total ? seg0 + PACK_SEG : total;
+    uint8_t *dst = out + out_off[j] + m.pref;
+    const uint8_t *slot = slots + u * slot_stride;
+    if (seg0 < m.a_len) {                                               // part of piece a
+        size_t e = seg1 < m.a_len ? seg1 : m.a_len;
+        group_copy(dst + seg0, slot + m.a_off + seg0, e - seg0, threadIdx.x, PACK_NT);
+    }
+    if (seg1 > m.a_len) {                                               // part of piece b
+        size_t s = seg0 > m.a_len ? seg0 : m.a_len;
+        group_copy(dst + s, slot + m.b_off + (s - m.a_len), seg1 - s, threadIdx.x, PACK_NT);
+    }
+}
+
+// ---- cdfini --------------------------------------------------------------------------------------------
+constexpr int    HIST_NT  = 256;
+constexpr size_t HIST_SEG = 1 << 20;
+
+// grid = (n_calls, segments of HIST_SEG bytes); hist = n_calls * 256 u64, zeroed by the caller
+__global__ void __launch_bounds__(HIST_NT)
+k_hist(const uint8_t *__restrict__ in, Geom g, unsigned long long *__restrict__ hist) {
+    __shared__ unsigned int h[256];
+    size_t cs, N; call_span(g, blockIdx.x, cs, N);
+    size_t s0 = (size_t)blockIdx.y * HIST_SEG;
+    if (s0 >= N) return;
+    size_t s1 = s0 + HIST_SEG < N ? s0 + HIST_SEG : N;
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint8_t *p = in + cs;
+    size_t a0 = s0, a1 = s1;
+    while (a0 < a1 && ((uintptr_t)(p + a0) & 15)) a0++;                 // unaligned head
+    size_t nv = (a1 - a0) >> 4;
+    for (size_t i = s0 + threadIdx.x; i < a0; i += HIST_NT) atomicAdd(&h[p[i]], 1u);
+    const uint4 *v = (const uint4 *)(p + a0);
+    for (size_t i = threadIdx.x; i < nv; i += HIST_NT) {
+        uint4 q = v[i];
+        uint32_t w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            atomicAdd(&h[w[k] & 0xff], 1u); atomicAdd(&h[(w[k] >> 8) & 0xff], 1u);
+            atomicAdd(&h[(w[k] >> 16) & 0xff], 1u); atomicAdd(&h[w[k] >> 24], 1u);
+        }
+    }
+    for (size_t i = a0 + (nv << 4) + threadIdx.x; i < a1; i += HIST_NT) atomicAdd(&h[p[i]], 1u);
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[(size_t)blockIdx.x * 256 + threadIdx.x], (unsigned long long)h[threadIdx.x]);
+}
+
+// one thread per call: the serial normalisation of rccdf.c:55-67
+__global__ void k_cdf_finalize(Geom g, const unsigned long long *__restrict__ hist, cdf_t *__restrict__ cdf, unsigned cdfnum,
+                               int *__restrict__ status) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= g.n_calls) return;
+    size_t cs, N; call_span(g, j, cs, N);
+    const unsigned long long *h = hist + j * 256;
+    cdf_t *c = cdf + j * CDF_STRIDE;
+    unsigned long long mx = 0, cum = 0; unsigned mxi = 0;
+    for (unsigned i = 0; i < cdfnum; i++) {
+        unsigned long long v = (h[i] << PROB_BITS) / N;
+        if (!v) v = 1;
+        cum += v;
+        if (v > mx) { mx = v; mxi = i; }
+    }
+    unsigned long long acc = 0; int bad = 0;
+    c[0] = 0;
+    for (unsigned i = 0; i < cdfnum; i++) {
+        unsigned long long v = (h[i] << PROB_BITS) / N;
+        if (!v) v = 1;
+        if (i == mxi) v -= cum - PROB_TOTAL;                            // adjust max (rccdf.c:60), wraps like the reference
+        unsigned prev = (cdf_t)acc;
+        acc += v;
+        c[i + 1] = (cdf_t)acc;
+        if (prev >= (cdf_t)acc) bad = 1;                                // the reference die()s here (rccdf.c:65)
+    }
+    if ((cdf_t)acc != (cdf_t)PROB_TOTAL) bad = 1;                       // rccdf.c:66
+    if (status) status[j] = bad ? -1 : 0;
+}
+
+}  // namespace trc

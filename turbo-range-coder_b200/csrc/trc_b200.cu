@@ -1,0 +1,387 @@
+// trc_b200.cu -- C ABI (include/trc_b200.h) over the sm_100a kernels.  No CPU code path exists: every entry
+// point launches kernels; failures surface as TRC_E_CUDA (batch layer) or a die()-style abort (drop-in layer).
+#include "../../include/trc_b200.h"
+#include "trc_common.cuh"
+#include "rans_static.cuh"
+#include "rc_static.cuh"
+#include "adaptive.cuh"
+#include "pack.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+using namespace trc;
+
+static thread_local char g_err[256] = "";
+static int g_dev = 0;
+static unsigned long long g_launches = 0;       // kernels launched by this library (bench.py reports the delta)
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    snprintf(g_err, sizeof g_err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return TRC_E_CUDA; } } while (0)
+#define CK_LAUNCH() do { g_launches++; CK(cudaPeekAtLastError()); } while (0)
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+struct Plan {
+    Geom g; int codec;
+    size_t slot_stride, rec_stride, o1_threads;
+    size_t off_meta, off_calls, off_slots, off_recs, off_o1, total;
+};
+
+static int make_plan(int codec, size_t total_len, size_t chunk_len, Plan &p) {
+    if (codec < 0 || codec >= NCODECS || total_len == 0 || chunk_len == 0) return TRC_E_ARG;
+    if ((chunk_len < total_len ? chunk_len : total_len) >= (1ull << 31)) return TRC_E_ARG;   // 32-bit lengths per call
+    p.codec = codec;
+    p.g = make_geom(codec, total_len, chunk_len);
+    const bool blocked = codec_blocked(codec);
+    p.slot_stride = (blocked && p.g.upc > 1) ? al16(4 * (size_t)p.g.unit_max + 64) : al16(p.g.unit_max) + 192;
+    p.rec_stride = blocked ? (((size_t)2 * p.g.unit_max + 3) & ~(size_t)3) + 16 : 0;
+    p.o1_threads = 0;
+    if (codec == ANS1) { size_t b = (p.g.n_units + AD_NT_BYTE - 1) / AD_NT_BYTE; if (b > 32) b = 32; p.o1_threads = b * AD_NT_BYTE; }
+    size_t o = 0;
+    p.off_meta = o;  o += al256(p.g.n_units * sizeof(UnitMeta));
+    p.off_calls = o; o += al256(p.g.n_calls * sizeof(CallInfo));
+    p.off_slots = o; o += al256(p.g.n_units * p.slot_stride);
+    p.off_recs = o;  o += al256(p.g.n_units * p.rec_stride * 4);
+    p.off_o1 = o;    o += al256(p.o1_threads * O1_TAB_WORDS * 4);
+    p.total = o;
+    return TRC_OK;
+}
+
+extern "C" {
+
+const char *trc_version(void) { return "trc_b200 0.1 (sm_100a)"; }
+const char *trc_last_error(void) { return g_err; }
+int trc_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+int trc_set_device(int dev) { g_dev = dev; CK(cudaSetDevice(dev)); return TRC_OK; }
+unsigned long long trc_launch_count(void) { return g_launches; }
+
+// Host-only check of the arithmetic the kernels rely on: for every frequency f in [1, 2^15] the table entry must
+// reproduce floor(s / f) for s at all multiples-of-f boundaries reachable after renormalisation (s < f << 16).
+int trc_selftest_host(void) {
+    int bad = 0;
+    for (uint32_t f = 1; f <= PROB_TOTAL; f++) {
+        uint4 e = rans_enc_entry(123, f);
+        const uint32_t smax = (uint32_t)(((uint64_t)f << 16) - 1);
+        auto chk = [&](uint32_t s) {
+            uint32_t q = (uint32_t)(((uint64_t)s * e.x) >> 32) >> (e.z >> 16);
+            uint32_t got = s + e.w + q * (e.z & 0xffffu);
+            uint32_t want = (s / f << PROB_BITS) + s % f + 123;
+            if (got != want) bad++;
+        };
+        for (uint32_t k = 1; k <= 65535; k += (f > 64 ? 257 : 1)) {
+            uint64_t b = (uint64_t)k * f;
+            if (b - 1 <= smax && b >= 2) chk((uint32_t)(b - 1));   // s >= 1 always
+            if (b <= smax) chk((uint32_t)b);
+            if (b + 1 <= smax) chk((uint32_t)(b + 1));
+        }
+        chk(smax); chk(smax - (f > 1 ? f - 1 : 0)); chk(f > 1 ? f : 1); chk(ANS_L < smax ? ANS_L : smax);
+    }
+    Geom g = make_geom(ANS, 9000001, 9000001);
+    if (g.n_calls != 1 || g.upc != 3 || g.n_units != 3) bad++;
+    size_t j, st, ln; uint32_t b;
+    unit_span(g, 2, j, b, st, ln); if (j != 0 || b != 2 || st != 2u * ANS_BLOCK || ln != 9000001 - 2u * ANS_BLOCK) bad++;
+    g = make_geom(RCS2, 10001, 4096);
+    if (g.n_calls != 3 || g.upc != 1) bad++;
+    call_span(g, 2, st, ln); if (st != 8192 || ln != 1809) bad++;
+    return bad;
+}
+
+size_t trc_num_chunks(size_t total_len, size_t chunk_len) { return chunk_len ? (total_len + chunk_len - 1) / chunk_len : 0; }
+size_t trc_enc_bound(size_t total_len, size_t chunk_len) { (void)chunk_len; return total_len + 64; }
+size_t trc_enc_scratch_bytes(int codec, size_t total_len, size_t chunk_len) {
+    Plan p; if (make_plan(codec, total_len, chunk_len, p) != TRC_OK) return 0; return p.total + 256;
+}
+
+int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, size_t chunk_len,
+                      const cdf_t *d_cdf, unsigned cdfnum, size_t chunks_per_cdf,
+                      unsigned char *d_out, uint64_t *d_out_off,
+                      void *d_scratch, size_t scratch_bytes, void *cuda_stream) {
+    Plan p; int rc = make_plan(codec, total_len, chunk_len, p);
+    if (rc != TRC_OK) return rc;
+    if (!d_in || !d_out || !d_out_off || !d_scratch) return TRC_E_ARG;
+    if (codec_static(codec) && (!d_cdf || cdfnum == 0 || cdfnum > 256)) return TRC_E_ARG;
+    uint8_t *sc = (uint8_t *)al256((size_t)d_scratch);
+    if ((size_t)(sc - (uint8_t *)d_scratch) + p.total > scratch_bytes) return TRC_E_NOMEM;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    UnitMeta *meta = (UnitMeta *)(sc + p.off_meta);
+    CallInfo *calls = (CallInfo *)(sc + p.off_calls);
+    uint8_t *slots = sc + p.off_slots;
+    uint32_t *recs = (uint32_t *)(sc + p.off_recs);
+    uint32_t *o1 = (uint32_t *)(sc + p.off_o1);
+    const Geom &g = p.g;
+    auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
+    switch (codec) {
+    case ANS4S: k_rans_static_enc<<<blocks(g.n_calls, RANS_S_NT), RANS_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
+    case RCS:   k_rc_static_enc<1><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
+    case RCS2:  k_rc_static_enc<2><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
+    case ANS4:  k_rans_adapt_enc<M_NIB, AD_NT_NIB><<<blocks(g.n_units, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta); break;
+    case ANS:   k_rans_adapt_enc<M_BYTE, AD_NT_BYTE><<<blocks(g.n_units, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta); break;
+    case ANS1:  k_rans_adapt_enc<M_O1, AD_NT_BYTE><<<(unsigned)(p.o1_threads / AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, o1, meta); break;
+    case RC:    k_rc_adapt_enc<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
+    case RCI:   k_rc_adapt_enc<R_BYTE2, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
+    case RC4:   k_rc_adapt_enc<R_NIB1, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
+    case RC4I:  k_rc_adapt_enc<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
+    }
+    CK_LAUNCH();
+    k_resolve_scan<<<1, SCAN_NT, 0, st>>>(g, codec_blocked(codec) ? 1 : 0, meta, calls, d_out_off);
+    CK_LAUNCH();
+    size_t seg = PACK_SEG_MIN;
+    while ((p.slot_stride + seg - 1) / seg > 65535) seg <<= 1;
+    dim3 pg((unsigned)g.n_units, (unsigned)((p.slot_stride + seg - 1) / seg));
+    k_pack<<<pg, PACK_NT, 0, st>>>(d_in, g, slots, p.slot_stride, meta, calls, d_out_off, d_out, seg);
+    CK_LAUNCH();
+    return TRC_OK;
+}
+
+int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in_off,
+                      unsigned char *d_out, size_t total_len, size_t chunk_len,
+                      const cdf_t *d_cdf, unsigned cdfnum, size_t chunks_per_cdf,
+                      unsigned flags, void *cuda_stream) {
+    Plan p; int rc = make_plan(codec, total_len, chunk_len, p);
+    if (rc != TRC_OK) return rc;
+    if (!d_in || !d_in_off || !d_out) return TRC_E_ARG;
+    if (codec_static(codec) && (!d_cdf || cdfnum == 0 || cdfnum > 256)) return TRC_E_ARG;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Geom g = p.g; g.upc = 1; g.n_units = g.n_calls;     // decoders work per call
+    auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
+    switch (codec) {
+    case ANS4S: k_rans_static_dec<<<blocks(g.n_calls, RANS_SD_NT), RANS_SD_NT, 0, st>>>(d_in, d_in_off, d_out, g, d_cdf, cdfnum, chunks_per_cdf, flags); break;
+    case RCS:   k_rc_static_dec<1><<<blocks(g.n_calls, RC_SD_NT), RC_SD_NT, 0, st>>>(d_in, d_in_off, d_out, g, d_cdf, cdfnum, chunks_per_cdf); break;
+    case RCS2:  k_rc_static_dec<2><<<blocks(g.n_calls, RC_SD_NT), RC_SD_NT, 0, st>>>(d_in, d_in_off, d_out, g, d_cdf, cdfnum, chunks_per_cdf); break;
+    case ANS4:  k_rans_adapt_dec<M_NIB, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g, nullptr, flags); break;
+    case ANS:   k_rans_adapt_dec<M_BYTE, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g, nullptr, flags); break;
+    case ANS1: {
+        size_t b = (g.n_calls + AD_NT_BYTE - 1) / AD_NT_BYTE; if (b > 32) b = 32;
+        uint32_t *o1 = nullptr;
+        CK(cudaMallocAsync((void **)&o1, b * AD_NT_BYTE * O1_TAB_WORDS * 4, st));
+        k_rans_adapt_dec<M_O1, AD_NT_BYTE><<<(unsigned)b, AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g, o1, flags);
+        g_launches++;
+        cudaError_t e = cudaPeekAtLastError();
+        cudaFreeAsync(o1, st);
+        CK(e);
+        return TRC_OK;
+    }
+    case RC:    k_rc_adapt_dec<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g); break;
+    case RCI:   k_rc_adapt_dec<R_BYTE2, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g); break;
+    case RC4:   k_rc_adapt_dec<R_NIB1, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
+    case RC4I:  k_rc_adapt_dec<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
+    }
+    CK_LAUNCH();
+    return TRC_OK;
+}
+
+int trc_cdfini_batch_dev(const unsigned char *d_in, size_t total_len, size_t chunk_len,
+                         cdf_t *d_cdf, unsigned cdfnum, int *d_status, void *cuda_stream) {
+    if (!d_in || !d_cdf || total_len == 0 || chunk_len == 0 || cdfnum == 0 || cdfnum > 256) return TRC_E_ARG;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    Geom g = make_geom(RCS, total_len, chunk_len);
+    unsigned long long *hist = nullptr;
+    CK(cudaMallocAsync((void **)&hist, g.n_calls * 256 * 8, st));
+    CK(cudaMemsetAsync(hist, 0, g.n_calls * 256 * 8, st));
+    size_t cl = chunk_len < total_len ? chunk_len : total_len;
+    dim3 hg((unsigned)g.n_calls, (unsigned)((cl + HIST_SEG - 1) / HIST_SEG));
+    k_hist<<<hg, HIST_NT, 0, st>>>(d_in, g, hist);
+    g_launches++;
+    k_cdf_finalize<<<(unsigned)((g.n_calls + 63) / 64), 64, 0, st>>>(g, hist, d_cdf, cdfnum, d_status);
+    g_launches++;
+    cudaError_t e = cudaPeekAtLastError();
+    cudaFreeAsync(hist, st);
+    CK(e);
+    return TRC_OK;
+}
+
+}  // extern "C"
+
+// ===========================================================================================================
+// Host-pointer layer: one lazily created context per process (device buffers grow, never shrink).
+// ===========================================================================================================
+namespace {
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int need(size_t n) {
+        if (n <= cap) return TRC_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t c = n + n / 8 + 4096;
+        if (cudaMalloc(&p, c) != cudaSuccess) { snprintf(g_err, sizeof g_err, "cudaMalloc(%zu) failed: %s", c, cudaGetErrorString(cudaGetLastError())); return TRC_E_NOMEM; }
+        cap = c; return TRC_OK;
+    }
+};
+struct Ctx {
+    std::mutex mu;
+    bool init = false;
+    cudaStream_t st = nullptr;
+    DevBuf in, out, off, cdf, scratch, status;
+    int ensure() {
+        if (init) return TRC_OK;
+        CK(cudaSetDevice(g_dev));
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        init = true; return TRC_OK;
+    }
+};
+Ctx g_ctx;
+
+int host_enc(int codec, const unsigned char *in, size_t total_len, size_t chunk_len, const cdf_t *cdf, unsigned cdfnum,
+             size_t chunks_per_cdf, unsigned char *out, uint64_t *out_off, size_t *out_len) {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    Ctx &c = g_ctx;
+    int rc = c.ensure(); if (rc) return rc;
+    Plan p; rc = make_plan(codec, total_len, chunk_len, p); if (rc) return rc;
+    const size_t n = p.g.n_calls;
+    if ((rc = c.in.need(total_len + 64)) || (rc = c.out.need(trc_enc_bound(total_len, chunk_len))) ||
+        (rc = c.off.need((n + 1) * 8)) || (rc = c.scratch.need(p.total + 256))) return rc;
+    CK(cudaMemcpyAsync(c.in.p, in, total_len, cudaMemcpyHostToDevice, c.st));
+    if (codec_static(codec)) {
+        if (!cdf) return TRC_E_ARG;
+        size_t nt = chunks_per_cdf ? (n + chunks_per_cdf - 1) / chunks_per_cdf : 1;
+        // the last table may be shorter than TRC_CDF_STRIDE entries in the caller's array
+        size_t bytes = ((nt - 1) * CDF_STRIDE + cdfnum + 1) * sizeof(cdf_t);
+        if ((rc = c.cdf.need(nt * CDF_STRIDE * sizeof(cdf_t)))) return rc;
+        CK(cudaMemcpyAsync(c.cdf.p, cdf, bytes, cudaMemcpyHostToDevice, c.st));
+    }
+    rc = trc_enc_batch_dev(codec, (const unsigned char *)c.in.p, total_len, chunk_len, (const cdf_t *)c.cdf.p, cdfnum, chunks_per_cdf,
+                           (unsigned char *)c.out.p, (uint64_t *)c.off.p, c.scratch.p, c.scratch.cap, c.st);
+    if (rc) return rc;
+    uint64_t total = 0;
+    if (out_off) {
+        CK(cudaMemcpyAsync(out_off, c.off.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c.st));
+        CK(cudaStreamSynchronize(c.st));
+        total = out_off[n];
+    } else {
+        CK(cudaMemcpyAsync(&total, (uint64_t *)c.off.p + n, 8, cudaMemcpyDeviceToHost, c.st));
+        CK(cudaStreamSynchronize(c.st));
+    }
+    CK(cudaMemcpyAsync(out, c.out.p, total, cudaMemcpyDeviceToHost, c.st));
+    CK(cudaStreamSynchronize(c.st));
+    if (out_len) *out_len = (size_t)total;
+    return TRC_OK;
+}
+
+// in_bytes: how many bytes of `in` to ship (== in_off[n] for the batch API)
+int host_dec(int codec, const unsigned char *in, const uint64_t *in_off, size_t in_bytes, unsigned char *out, size_t total_len,
+             size_t chunk_len, const cdf_t *cdf, unsigned cdfnum, size_t chunks_per_cdf, unsigned flags) {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    Ctx &c = g_ctx;
+    int rc = c.ensure(); if (rc) return rc;
+    Plan p; rc = make_plan(codec, total_len, chunk_len, p); if (rc) return rc;
+    const size_t n = p.g.n_calls;
+    if ((rc = c.in.need(in_bytes + 64)) || (rc = c.out.need(total_len + 64)) || (rc = c.off.need((n + 1) * 8))) return rc;
+    CK(cudaMemcpyAsync(c.off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, c.st));
+    CK(cudaMemcpyAsync(c.in.p, in, in_bytes, cudaMemcpyHostToDevice, c.st));
+    if (codec_static(codec)) {
+        if (!cdf) return TRC_E_ARG;
+        size_t nt = chunks_per_cdf ? (n + chunks_per_cdf - 1) / chunks_per_cdf : 1;
+        size_t bytes = ((nt - 1) * CDF_STRIDE + cdfnum + 1) * sizeof(cdf_t);
+        if ((rc = c.cdf.need(nt * CDF_STRIDE * sizeof(cdf_t)))) return rc;
+        CK(cudaMemcpyAsync(c.cdf.p, cdf, bytes, cudaMemcpyHostToDevice, c.st));
+    }
+    rc = trc_dec_batch_dev(codec, (const unsigned char *)c.in.p, (const uint64_t *)c.off.p, (unsigned char *)c.out.p, total_len, chunk_len,
+                           (const cdf_t *)c.cdf.p, cdfnum, chunks_per_cdf, flags, c.st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, c.out.p, total_len, cudaMemcpyDeviceToHost, c.st));
+    CK(cudaStreamSynchronize(c.st));
+    return TRC_OK;
+}
+
+[[noreturn]] void die_cuda(const char *fn, int rc) {          // mirrors die() include_/conf.h:379
+    fprintf(stderr, "trc_b200: %s failed (%d): %s\n", fn, rc, g_err);
+    fflush(stderr);
+    exit(-1);
+}
+
+// drop-in encoder: the whole buffer is one call
+size_t dropin_enc(const char *fn, int codec, unsigned char *in, size_t inlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum) {
+    if (inlen == 0) {
+        // reference on an empty buffer: the rANS codecs write nothing; a single range coder still flushes one
+        // word (low += 2^32 -> 0x00000001, turborc_.h:120-122); the 2-coder forms dereference wild pointers.
+        if (codec == RCS || codec == RC || codec == RC4) { uint32_t one = 1; memcpy(out, &one, 4); return 4; }
+        return 0;
+    }
+    size_t l = 0;
+    int rc = host_enc(codec, in, inlen, inlen, cdf, cdfnum, 0, out, nullptr, &l);
+    if (rc) die_cuda(fn, rc);
+    return l;
+}
+// drop-in decoder.  The reference decoders are never given the compressed length; a valid stream is shorter
+// than outlen (otherwise the encoder returned a raw copy and the caller must not decode, turborc.c:434), and the
+// encoder's contract already makes that buffer at least outlen bytes, so outlen bytes of `in` are shipped.
+size_t dropin_dec(const char *fn, int codec, unsigned char *in, size_t outlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum, unsigned flags) {
+    if (outlen == 0) return 0;
+    uint64_t off[2] = { 0, (uint64_t)outlen + 8 };             // != outlen, so the call is never taken for raw
+    {
+        std::lock_guard<std::mutex> lk(g_ctx.mu);
+        int rc = g_ctx.ensure(); if (rc) die_cuda(fn, rc);
+        if ((rc = g_ctx.in.need(outlen + 64))) die_cuda(fn, rc);
+        if (cudaMemsetAsync((uint8_t *)g_ctx.in.p + outlen, 0, 64, g_ctx.st) != cudaSuccess) die_cuda(fn, TRC_E_CUDA);
+    }
+    int rc = host_dec(codec, in, off, outlen, out, outlen, outlen, cdf, cdfnum, 0, flags);
+    if (rc) die_cuda(fn, rc);
+    return outlen;
+}
+}  // namespace
+
+extern "C" {
+
+int trc_enc_batch_host(int codec, const unsigned char *in, size_t total_len, size_t chunk_len,
+                       const cdf_t *cdf, unsigned cdfnum, size_t chunks_per_cdf,
+                       unsigned char *out, uint64_t *out_off, size_t *out_len) {
+    if (!in || !out) return TRC_E_ARG;
+    return host_enc(codec, in, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, out, out_off, out_len);
+}
+int trc_dec_batch_host(int codec, const unsigned char *in, const uint64_t *in_off,
+                       unsigned char *out, size_t total_len, size_t chunk_len,
+                       const cdf_t *cdf, unsigned cdfnum, size_t chunks_per_cdf, unsigned flags) {
+    if (!in || !in_off || !out || !chunk_len) return TRC_E_ARG;
+    size_t n = trc_num_chunks(total_len, chunk_len);
+    return host_dec(codec, in, in_off, (size_t)in_off[n], out, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, flags);
+}
+
+// ---- drop-in layer ----------------------------------------------------------------------------------------
+void anscdfini(unsigned id) { (void)id; std::lock_guard<std::mutex> lk(g_ctx.mu); int rc = g_ctx.ensure(); if (rc) die_cuda("anscdfini", rc); }
+
+#define ENC3(name, codec) size_t name(unsigned char *in, size_t inlen, unsigned char *out) { return dropin_enc(#name, codec, in, inlen, out, nullptr, 0); }
+#define DEC3(name, codec, fl) size_t name(unsigned char *in, size_t outlen, unsigned char *out) { return dropin_dec(#name, codec, in, outlen, out, nullptr, 0, fl); }
+// static nibble rANS: the drop-in contract is a 16-symbol alphabet with a cdf_t[>=17] table (anscdf.c:57)
+#define ENC4S(name) size_t name(unsigned char *in, size_t inlen, unsigned char *out, cdf_t *cdf) { return dropin_enc(#name, ANS4S, in, inlen, out, cdf, 16); }
+#define DEC4S(name) size_t name(unsigned char *in, size_t outlen, unsigned char *out, cdf_t *cdf) { return dropin_dec(#name, ANS4S, in, outlen, out, cdf, 16, TRC_F_REF_TAIL); }
+ENC4S(anscdf4senc) ENC4S(anscdf4sencs) ENC4S(anscdf4sencx)
+DEC4S(anscdf4sdec) DEC4S(anscdf4sdecs) DEC4S(anscdf4sdecx)
+ENC3(anscdf4enc, ANS4) ENC3(anscdf4encs, ANS4) ENC3(anscdf4encx, ANS4)
+DEC3(anscdf4dec, ANS4, TRC_F_REF_TAIL) DEC3(anscdf4decs, ANS4, TRC_F_REF_TAIL) DEC3(anscdf4decx, ANS4, TRC_F_REF_TAIL)
+ENC3(anscdfenc, ANS) ENC3(anscdfencs, ANS) ENC3(anscdfencx, ANS)
+DEC3(anscdfdec, ANS, 0) DEC3(anscdfdecs, ANS, 0) DEC3(anscdfdecx, ANS, 0)
+ENC3(anscdf1enc, ANS1) ENC3(anscdf1encs, ANS1) ENC3(anscdf1encx, ANS1)
+DEC3(anscdf1dec, ANS1, 0) DEC3(anscdf1decs, ANS1, 0) DEC3(anscdf1decx, ANS1, 0)
+ENC3(rccdfenc, RC) DEC3(rccdfdec, RC, 0)
+ENC3(rccdfienc, RCI) DEC3(rccdfidec, RCI, 0)
+ENC3(rccdf4enc, RC4) DEC3(rccdf4dec, RC4, 0)
+ENC3(rccdf4ienc, RC4I) DEC3(rccdf4idec, RC4I, 0)
+
+#define ENC5(name, codec) size_t name(unsigned char *in, size_t inlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum) { return dropin_enc(#name, codec, in, inlen, out, cdf, cdfnum); }
+#define DEC5(name, codec) size_t name(unsigned char *in, size_t outlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum) { return dropin_dec(#name, codec, in, outlen, out, cdf, cdfnum, 0); }
+ENC5(rccdfsenc, RCS) DEC5(rccdfsbdec, RCS) DEC5(rccdfsldec, RCS)          // linear and binary search find the same symbol
+ENC5(rccdfs2enc, RCS2) DEC5(rccdfsb2dec, RCS2) DEC5(rccdfsl2dec, RCS2)
+
+int cdfini(unsigned char *in, size_t inlen, cdf_t *cdf, unsigned cdfnum) {
+    if (inlen == 0 || cdfnum == 0 || cdfnum > 256) { fprintf(stderr, "Fatal cdf: empty input\n"); exit(-1); }
+    int status = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx.mu);
+        Ctx &c = g_ctx;
+        int rc = c.ensure(); if (rc) die_cuda("cdfini", rc);
+        if ((rc = c.in.need(inlen + 64)) || (rc = c.cdf.need(CDF_STRIDE * sizeof(cdf_t))) || (rc = c.status.need(64))) die_cuda("cdfini", rc);
+        if (cudaMemcpyAsync(c.in.p, in, inlen, cudaMemcpyHostToDevice, c.st) != cudaSuccess) die_cuda("cdfini", TRC_E_CUDA);
+        rc = trc_cdfini_batch_dev((const unsigned char *)c.in.p, inlen, inlen, (cdf_t *)c.cdf.p, cdfnum, (int *)c.status.p, c.st);
+        if (rc) die_cuda("cdfini", rc);
+        if (cudaMemcpyAsync(cdf, c.cdf.p, (cdfnum + 1) * sizeof(cdf_t), cudaMemcpyDeviceToHost, c.st) != cudaSuccess ||
+            cudaMemcpyAsync(&status, c.status.p, sizeof(int), cudaMemcpyDeviceToHost, c.st) != cudaSuccess ||
+            cudaStreamSynchronize(c.st) != cudaSuccess) die_cuda("cdfini", TRC_E_CUDA);
+    }
+    if (status) { fprintf(stderr, "Fatal cdf\n"); fflush(stderr); exit(-1); }     // die() rccdf.c:65-66
+    return (int)inlen;
+}
+
+}  // extern "C"
