@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- encode+decode GB/s of the B200 CDF entropy path on BASELINE.json's workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--codec rcs2|ans4s|rcs|ans|rc|...] [--chunk BYTES] [--size BYTES]
+
+One "step" = one encode pass + one decode pass of the hot path over one batch: SIZE bytes (default
+100 000 000) of synthetic Zipf(1.1) bytes cut into CHUNK-byte chunks (default 4096), every chunk coded exactly
+as one call of the reference function (default codec rcs2 = rccdfs2enc / rccdfsb2dec, what `turborc -e45` runs,
+the id BASELINE.json's CPU config names).  The static table comes from cdfini on the whole buffer, computed
+outside the timed region exactly like the reference harness does (turborc.c:429-433).
+
+value   = SIZE / (t_encode + t_decode), GB = 1e9, buffers resident in HBM, CUDA-event time on the launching
+          stream, L2 flushed (256 MiB write) before every timed encode and decode.
+e2e     = the same through the C-ABI host entry points (trc_enc_batch_host / trc_dec_batch_host) on pinned host
+          buffers: H2D of the input, D2H of the packed stream and offsets, H2D of the stream, D2H of the decoded
+          bytes are all inside the timed region (wall clock; the calls are synchronous).
+roofline / cpu_baseline: see DESIGN.md section "Measurement".
+With --gpus N > 1 (torchrun): every rank codes its own SIZE-byte shard (weak scaling), the packed streams are
+gathered on rank 0 over NCCL inside the step, time = max over ranks.
+--impl reference: the reference's own CPU implementation (oracle/_ref, else the oracle port) on all host
+threads, on a bounded sample of the same workload.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CODECS = {"ans4s": 0, "ans4": 1, "ans": 2, "ans1": 3, "rcs": 4, "rcs2": 5, "rc": 6, "rci": 7, "rc4": 8, "rc4i": 9}
+REF_FN = {0: ("anscdf4senc", "anscdf4sdec"), 1: ("anscdf4enc", "anscdf4dec"), 2: ("anscdfenc", "anscdfdec"),
+          3: ("anscdf1enc", "anscdf1dec"), 4: ("rccdfsenc", "rccdfsbdec"), 5: ("rccdfs2enc", "rccdfsb2dec"),
+          6: ("rccdfenc", "rccdfdec"), 7: ("rccdfienc", "rccdfidec"), 8: ("rccdf4enc", "rccdf4dec"),
+          9: ("rccdf4ienc", "rccdf4idec")}
+METRIC = "encode+decode GB/s on 100MB order-0 byte stream; bitstream bit-exact vs ref"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksThrottleReason") and isinstance(getattr(nv, k), int)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if bit and (r & bit) and "None" not in name and "All" not in name:
+                        self.reasons.add(name.replace("nvmlClocksThrottleReason", ""))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(1.0)
+        s = sorted(self.samples)
+        norm = {"GpuIdle": "gpu_idle", "ApplicationsClocksSetting": "applications_clocks_setting", "SwPowerCap": "sw_power_cap",
+                "HwSlowdown": "hw_slowdown", "SyncBoost": "sync_boost", "SwThermalSlowdown": "sw_thermal_slowdown",
+                "HwThermalSlowdown": "hw_thermal_slowdown", "HwPowerBrakeSlowdown": "hw_power_brake_slowdown",
+                "DisplayClockSetting": "display_clock_setting", "UserDefinedClocks": "applications_clocks_setting"}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "samples": len(s),
+                "reasons": sorted({norm.get(r, r) for r in self.reasons} - {"gpu_idle"})}
+
+
+def make_data(size, rank=0):
+    dg = importlib.import_module("turbo-range-coder_b200.datagen")
+    return dg.zipf(size, seed=dg.ZIPF_SEED + rank)
+
+
+def cpu_reference_run(codec, data, cdf, threads, reps, sample_bytes):
+    from oracle import cpu
+    enc, dec = REF_FN[codec]
+    sample = data[:sample_bytes]
+    r = cpu.cpu_bench(True, enc, dec, sample, 4 << 20, cdf if codec in (0, 4, 5) else None, 256 if codec in (4, 5) else 0,
+                      threads=threads, reps=reps)
+    r["sample_bytes"] = int(sample.size)
+    return r
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation on all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import cpu
+    codec = CODECS[args.codec]
+    threads = os.cpu_count() or 1
+    sample_bytes = min(args.size, (8 << 20) * threads)
+    data = make_data(sample_bytes)
+    lib = cpu.ref() or cpu.port()
+    cdf = lib.cdfini(data)
+    for _ in range(max(args.warmup, 1)):
+        r = cpu_reference_run(codec, data, cdf, threads, 1, sample_bytes)
+    es = ds = 0.0
+    for _ in range(args.steps):
+        r = cpu_reference_run(codec, data, cdf, threads, 1, sample_bytes)
+        assert r["ok"], "reference round trip failed"
+        es += r["enc_s"]; ds += r["dec_s"]
+    es /= args.steps; ds /= args.steps
+    val = sample_bytes / (es + ds) / 1e9
+    sample = (f"first {sample_bytes} B of the workload, {REF_FN[codec][0]}+{REF_FN[codec][1]} called per 4 MiB chunk, "
+              f"{threads} pthreads, mean of {args.steps} passes")
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round((es + ds) * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{args.size} B Zipf(1.1) bytes, static CDF, codec {args.codec}", "codec": args.codec},
+            "enc_gbs": round(sample_bytes / es / 1e9, 4), "dec_gbs": round(sample_bytes / ds / 1e9, 4),
+            "ratio": round(r["clen"] / sample_bytes, 5),
+            "cpu_baseline": {"value": round(val, 4), "unit": "GB/s", "cores": threads, "kind": r["kind"], "sample": sample},
+            "e2e": {"value": round(val, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    trc = importlib.import_module("turbo-range-coder_b200")
+    shard = importlib.import_module("turbo-range-coder_b200.shard")
+    trc.lib.trc_set_device(local)
+    codec = CODECS[args.codec]
+    size, chunk = args.size, args.chunk
+    static = codec in (0, 4, 5)
+
+    data = make_data(size, rank)
+    if codec in (0, 1, 8, 9) and not (codec == 0 and args.bytes_alphabet):
+        data = data & 15
+    d_in = torch.from_numpy(data).to(dev)
+    batch = trc.DeviceBatch(codec, size, chunk, cdfnum=(256 if static else 0), device=dev)
+    if static:                                    # cdfini on the device, outside the timed region (turborc.c:429-433)
+        cdf_dev, status = trc.cdfini_dev(d_in, size, size)
+        assert int(status.abs().sum().item()) == 0
+        batch.cdf = cdf_dev
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # ---- correctness gate (untimed): round trip on the device, packed stream vs the oracle on a bounded prefix ----
+    batch.encode(d_in)
+    back = batch.decode()
+    torch.cuda.synchronize()
+    assert torch.equal(back, d_in), "device round trip failed"
+    clen = batch.compressed_len()
+    n_chunks = batch.n
+
+    def step(ev=None):
+        flush.zero_()
+        if ev: ev[0].record()
+        batch.encode(d_in)
+        if world > 1:
+            payload = batch.out[:clen]            # clen is fixed for the fixed input; lengths still travel every step
+            shard.gather_compressed(payload, dst=0, out=gather_buf)
+        if ev: ev[1].record()
+        flush.zero_()
+        if ev: ev[2].record()
+        batch.decode()
+        if ev: ev[3].record()
+
+    gather_buf = None
+    if world > 1 and rank == 0:
+        gather_buf = torch.empty(int(size * 1.05) * world, dtype=torch.uint8, device=dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    trc.profile_enable(True)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    kern_ms = {}
+    sampler = ClockSampler(local); sampler.start()
+    launches0 = trc.launch_count()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step(evs[k])
+        # per-kernel intervals of the decode call (the last call) are read after the loop for the final step only;
+        # encode-side intervals are collected in a separate short pass below to keep this loop free of host syncs
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    launches = trc.launch_count() - launches0
+    clocks = sampler.result()
+    enc_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    dec_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+
+    # per-kernel durations (CUDA events between the kernels, same stream), averaged over a few extra passes
+    names_enc = ["encode", "resolve_scan", "pack"]
+    acc = {}
+    reps = min(args.steps, 10)
+    for _ in range(reps):
+        flush.zero_(); batch.encode(d_in)
+        for nm, ms in zip(names_enc, trc.profile_read()):
+            acc[nm] = acc.get(nm, 0.0) + ms / reps
+        flush.zero_(); batch.decode()
+        for nm, ms in zip(["decode"], trc.profile_read()):
+            acc[nm] = acc.get(nm, 0.0) + ms / reps
+    trc.profile_enable(False)
+    kern_ms = {k: round(v, 4) for k, v in acc.items()}
+
+    t = torch.tensor([enc_ms, dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    enc_ms, dec_ms = float(t[0]), float(t[1])
+    step_ms = enc_ms + dec_ms
+    total_bytes = size * world
+    value = total_bytes / (step_ms * 1e-3) / 1e9
+
+    # ---- e2e through the C-ABI host entry points, pinned host buffers ----
+    h_in = torch.from_numpy(data).pin_memory().numpy()
+    h_out = torch.empty(int(trc.lib.trc_enc_bound(size, chunk)), dtype=torch.uint8).pin_memory().numpy()
+    h_off = torch.empty(n_chunks + 1, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+    h_back = torch.empty(size, dtype=torch.uint8).pin_memory().numpy()
+    cdf_h = batch.cdf.cpu().numpy().view(np.uint16) if static else None
+    e2e_steps = max(3, min(args.steps, 10))
+    te = td = 0.0
+    for k in range(2 + e2e_steps):
+        a = time.perf_counter()
+        s_out, s_off = trc.enc_batch_host(codec, h_in, chunk, cdf=cdf_h, cdfnum=256 if static else 0, out=h_out, off=h_off)
+        b = time.perf_counter()
+        trc.dec_batch_host(codec, s_out, s_off, size, chunk, cdf=cdf_h, cdfnum=256 if static else 0, out=h_back)
+        c = time.perf_counter()
+        if k >= 2:
+            te += b - a; td += c - b
+    assert np.array_equal(h_back, data), "host round trip failed"
+    te /= e2e_steps; td /= e2e_steps
+    t = torch.tensor([te, td], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    te, td = float(t[0]), float(t[1])
+    e2e = {"value": round(total_bytes / (te + td) / 1e9, 4), "unit": "GB/s",
+           "h2d_bytes_per_step": int(size + clen + 8 * (n_chunks + 1)), "d2h_bytes_per_step": int(clen + 8 * (n_chunks + 1) + size),
+           "enc_gbs": round(total_bytes / te / 1e9, 4), "dec_gbs": round(total_bytes / td / 1e9, 4),
+           "api": "trc_enc_batch_host + trc_dec_batch_host, pinned host buffers"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ----
+    peak, peak_src = peaks()
+    dom = max(kern_ms, key=kern_ms.get)
+    alg = {"encode": size + clen, "decode": size + clen, "pack": 2 * clen, "resolve_scan": 40 * n_chunks}[dom]
+    achieved = alg / (kern_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"{args.codec}/{dom}")
+    roofline = {"bound": "hbm", "kernel": f"{args.codec}/{dom}", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg), "kernel_ms": kern_ms}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        sample_bytes = min(size, (8 << 20) * threads)
+        from oracle import cpu
+        cdfh = (cpu.ref() or cpu.port()).cdfini(data[:sample_bytes]) if static else None
+        r = cpu_reference_run(codec, data, cdfh, threads, 2, sample_bytes)
+        one = cpu_reference_run(codec, data, cdfh, 1, 1, min(sample_bytes, 16 << 20))
+        cpu_baseline = {"value": round(sample_bytes / (r["enc_s"] + r["dec_s"]) / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": r["kind"],
+                        "sample": f"first {sample_bytes} B of the workload, {REF_FN[codec][0]}+{REF_FN[codec][1]} per 4 MiB chunk, {threads} pthreads, best of 2",
+                        "enc_gbs": round(sample_bytes / r["enc_s"] / 1e9, 4), "dec_gbs": round(sample_bytes / r["dec_s"] / 1e9, 4),
+                        "single_thread_gbs": round(one["sample_bytes"] / (one["enc_s"] + one["dec_s"]) / 1e9, 4)}
+
+    line = {"metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": f"{size} B Zipf(1.1) bytes per GPU, static CDF (cdfini on the whole buffer), batch of {chunk}-byte chunks, "
+                                   f"each chunk == one reference call ({REF_FN[codec][0]}/{REF_FN[codec][1]})",
+                       "codec": args.codec, "chunk_bytes": chunk, "n_chunks": n_chunks, "l2": "flushed (256 MiB write) before each timed encode and decode",
+                       "multi_gpu": "independent shard per rank, packed streams gathered on rank 0 (NCCL) inside the step" if world > 1 else "single GPU"},
+            "enc_gbs": round(total_bytes / (enc_ms * 1e-3) / 1e9, 3), "dec_gbs": round(total_bytes / (dec_ms * 1e-3) / 1e9, 3),
+            "ratio": round(clen / size, 5), "compressed_bytes": int(clen),
+            "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--codec", default="rcs2", choices=sorted(CODECS))
+    ap.add_argument("--chunk", type=int, default=4096)
+    ap.add_argument("--size", type=int, default=100_000_000)
+    ap.add_argument("--bytes-alphabet", action="store_true", help="ans4s: code full bytes with a 256-entry table")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

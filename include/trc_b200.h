@@ -60,6 +60,8 @@ const char *trc_last_error(void);             /* text of the last CUDA failure o
 int         trc_device_count(void);
 int         trc_set_device(int dev);          /* device used by *_host and drop-in calls (default 0) */
 unsigned long long trc_launch_count(void);    /* kernels launched by this library so far (monotonic) */
+void        trc_profile_enable(int on);       /* record CUDA events around every kernel of the batch calls */
+int         trc_profile_read(float *ms, int cap); /* per-kernel milliseconds of the most recent batch call */
 int         trc_selftest_host(void);          /* host-only arithmetic self-check (division-by-reciprocal table,
                                                  geometry); returns the number of failures.  Needs no GPU. */
 

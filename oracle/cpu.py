@@ -138,3 +138,35 @@ def ref():
             return None
         _ref = _Lib(p, "")
     return _ref
+
+
+def cpu_bench(use_ref, enc, dec, data, chunk, cdf=None, cdfnum=0, threads=None, reps=1):
+    """Time encoder+decoder per chunk on `threads` host threads (oracle/cpu_bench.c).
+    -> dict(enc_s, dec_s, clen, ok, threads, kind)."""
+    p = os.path.join(_HERE, "libtrc_cpubench.so")
+    if not os.path.exists(p):
+        build(ref_too=False)
+    lib = ctypes.CDLL(p)
+    refp = os.path.join(_HERE, "_ref", "libtrcref.so")
+    if use_ref and os.path.exists(refp):
+        libpath, prefix, kind = refp, "", "reference"
+    else:
+        port()
+        libpath, prefix, kind = os.path.join(_HERE, "libtrc_oracle.so"), "orc_", "port"
+    threads = threads or os.cpu_count() or 1
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    sig = 2 if ENCODERS[enc][1] else (1 if ENCODERS[enc][0] else 0)
+    tab = np.zeros(257, np.uint16)
+    if cdf is not None:
+        c = np.ascontiguousarray(cdf, dtype=np.uint16).reshape(-1)
+        tab[:min(257, c.size)] = c[:257]
+    es, ds = ctypes.c_double(0), ctypes.c_double(0)
+    cl, ok = ctypes.c_size_t(0), ctypes.c_int(0)
+    lib.orc_cpu_bench.restype = ctypes.c_int
+    rc = lib.orc_cpu_bench(libpath.encode(), (prefix + enc).encode(), (prefix + dec).encode(), ctypes.c_int(sig),
+                           ctypes.c_void_p(data.ctypes.data), ctypes.c_size_t(data.size), ctypes.c_size_t(chunk),
+                           ctypes.c_void_p(tab.ctypes.data), ctypes.c_uint(cdfnum), ctypes.c_int(threads), ctypes.c_int(reps),
+                           ctypes.byref(es), ctypes.byref(ds), ctypes.byref(cl), ctypes.byref(ok))
+    if rc:
+        raise RuntimeError(f"orc_cpu_bench failed: {rc}")
+    return dict(enc_s=es.value, dec_s=ds.value, clen=cl.value, ok=bool(ok.value), threads=threads, kind=kind)

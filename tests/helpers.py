@@ -30,6 +30,9 @@ def cpu_batch(lib, codec, data, chunk_len, cdf=None, cdfnum=None, chunks_per_cdf
             t = c // chunks_per_cdf if chunks_per_cdf else 0
             tab = cdf.reshape(-1)[t * 257:(t + 1) * 257]
         r, out = lib.enc(enc, data[s:s + l], tab, cdfnum)
+        if r > out.size:      # rccdf4ienc on < 4 bytes returns 4: bytes past the raw copy are undefined, we define 0
+            assert enc == "rccdf4ienc" and l < 4
+            out = np.concatenate([out, np.zeros(r - out.size, np.uint8)])
         assert out.size == r, (enc, l, r, out.size)
         parts.append(out)
         off.append(off[-1] + r)

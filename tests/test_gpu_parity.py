@@ -28,8 +28,11 @@ def _check_batch(trc, port, codec, d, chunk_len, label):
     assert np.array_equal(goff, woff), (label, enc, chunk_len, "offsets", first_diff(goff, woff))
     assert np.array_equal(got, want), (label, enc, chunk_len, "bytes differ at", first_diff(got, want))
     # decode what we produced
-    quirk = any(int(woff[c + 1] - woff[c]) < l and np.array_equal(want[int(woff[c]):int(woff[c + 1])], d[s:s + int(woff[c + 1] - woff[c])])
-                for c, (s, l) in enumerate(chunks(d.size, chunk_len)))
+    def _quirk(c, s, l):
+        r = int(woff[c + 1] - woff[c])
+        k = min(r, l)
+        return r != l and np.array_equal(want[int(woff[c]):int(woff[c]) + k], d[s:s + k])
+    quirk = codec == 9 and any(_quirk(c, s, l) for c, (s, l) in enumerate(chunks(d.size, chunk_len)))
     if quirk:                                   # rccdf4ienc raw-with-short-length: not decodable, by the reference either
         return
     back = trc.dec_batch_host(codec, got, goff, d.size, chunk_len, cdf=cdf, cdfnum=num)
@@ -41,7 +44,7 @@ def _check_batch(trc, port, codec, d, chunk_len, label):
             if b - a == l:
                 assert np.array_equal(back[s:s + l], d[s:s + l])
             else:
-                exp = port.dec(dec, got[a:b], l, cdf, num)
+                exp = port.dec(dec, got[a:], l, cdf, num)     # garbage tails over-read: give both the same bytes
                 assert np.array_equal(back[s:s + l], exp), (label, dec, "ref tail", c)
 
 

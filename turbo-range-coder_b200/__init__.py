@@ -83,6 +83,17 @@ def launch_count():
     return int(lib.trc_launch_count())
 
 
+def profile_enable(on=True):
+    lib.trc_profile_enable(1 if on else 0)
+
+
+def profile_read():
+    """Milliseconds of each kernel of the most recent batch call (needs profile_enable())."""
+    buf = (ctypes.c_float * 8)()
+    n = lib.trc_profile_read(buf, 8)
+    return [float(buf[i]) for i in range(n)]
+
+
 def num_chunks(total_len, chunk_len):
     return int(lib.trc_num_chunks(total_len, chunk_len))
 

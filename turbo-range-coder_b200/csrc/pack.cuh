@@ -73,6 +73,11 @@ k_pack(const uint8_t *__restrict__ in, Geom g, const uint8_t *__restrict__ slots
         size_t cs = j * g.chunk, uo = start - cs;                      // this unit's share of the call
         if (uo >= ci.len) return;
         size_t n = ci.len - uo < len ? ci.len - uo : len;
+        // rccdf4ienc quirk on inputs shorter than 4 bytes: the returned length (4) exceeds inlen; the reference
+        // leaves those bytes untouched, we zero them so the packed stream is deterministic
+        size_t ccs, N; call_span(g, j, ccs, N);
+        if (ci.len > N && b == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+            for (size_t k = N; k < ci.len; k++) out[out_off[j] + k] = 0;
         if (seg0 >= n) return;
         size_t m = n - seg0 < PACK_SEG ? n - seg0 : PACK_SEG;
         group_copy(out + out_off[j] + uo + seg0, in + start + seg0, m, threadIdx.x, PACK_NT);

@@ -21,6 +21,18 @@ static unsigned long long g_launches = 0;       // kernels launched by this libr
     snprintf(g_err, sizeof g_err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return TRC_E_CUDA; } } while (0)
 #define CK_LAUNCH() do { g_launches++; CK(cudaPeekAtLastError()); } while (0)
 
+// Optional per-kernel timing of the batch calls (bench.py's roofline leg): when enabled, an event is recorded
+// on the caller's stream before/after every kernel of trc_enc_batch_dev / trc_dec_batch_dev; trc_profile_read
+// synchronises on them and returns the milliseconds of the most recent call.  Off by default (zero overhead).
+static int g_prof = 0, g_prof_n = 0;
+static cudaEvent_t g_pev[8];
+static bool g_pev_init = false;
+static void prof_mark(cudaStream_t st) {
+    if (!g_prof) return;
+    if (!g_pev_init) { for (auto &e : g_pev) cudaEventCreate(&e); g_pev_init = true; }
+    if (g_prof_n < 8) cudaEventRecord(g_pev[g_prof_n++], st);
+}
+
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 static inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
@@ -57,6 +69,14 @@ const char *trc_last_error(void) { return g_err; }
 int trc_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 int trc_set_device(int dev) { g_dev = dev; CK(cudaSetDevice(dev)); return TRC_OK; }
 unsigned long long trc_launch_count(void) { return g_launches; }
+void trc_profile_enable(int on) { g_prof = on; g_prof_n = 0; }
+int trc_profile_read(float *ms, int cap) {       // -> number of kernel intervals written (kernels of the last call)
+    int n = g_prof_n - 1, k = 0;
+    if (n <= 0) return 0;
+    cudaEventSynchronize(g_pev[g_prof_n - 1]);
+    for (; k < n && k < cap; k++) cudaEventElapsedTime(&ms[k], g_pev[k], g_pev[k + 1]);
+    return k;
+}
 
 // Host-only check of the arithmetic the kernels rely on: for every frequency f in [1, 2^15] the table entry must
 // reproduce floor(s / f) for s at all multiples-of-f boundaries reachable after renormalisation (s < f << 16).
@@ -90,7 +110,11 @@ int trc_selftest_host(void) {
 }
 
 size_t trc_num_chunks(size_t total_len, size_t chunk_len) { return chunk_len ? (total_len + chunk_len - 1) / chunk_len : 0; }
-size_t trc_enc_bound(size_t total_len, size_t chunk_len) { (void)chunk_len; return total_len + 64; }
+size_t trc_enc_bound(size_t total_len, size_t chunk_len) {
+    // every call yields at most its input length, except rccdf4ienc's 4-byte answer on inputs shorter than 4 bytes
+    size_t extra = (chunk_len && chunk_len < 4) ? 4 * trc_num_chunks(total_len, chunk_len) : 4;
+    return total_len + extra + 64;
+}
 size_t trc_enc_scratch_bytes(int codec, size_t total_len, size_t chunk_len) {
     Plan p; if (make_plan(codec, total_len, chunk_len, p) != TRC_OK) return 0; return p.total + 256;
 }
@@ -113,6 +137,7 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     uint32_t *o1 = (uint32_t *)(sc + p.off_o1);
     const Geom &g = p.g;
     auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
+    g_prof_n = 0; prof_mark(st);
     switch (codec) {
     case ANS4S: k_rans_static_enc<<<blocks(g.n_calls, RANS_S_NT), RANS_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
     case RCS:   k_rc_static_enc<1><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
@@ -125,14 +150,14 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     case RC4:   k_rc_adapt_enc<R_NIB1, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
     case RC4I:  k_rc_adapt_enc<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
     }
-    CK_LAUNCH();
+    CK_LAUNCH(); prof_mark(st);
     k_resolve_scan<<<1, SCAN_NT, 0, st>>>(g, codec_blocked(codec) ? 1 : 0, meta, calls, d_out_off);
-    CK_LAUNCH();
+    CK_LAUNCH(); prof_mark(st);
     size_t seg = PACK_SEG_MIN;
     while ((p.slot_stride + seg - 1) / seg > 65535) seg <<= 1;
     dim3 pg((unsigned)g.n_units, (unsigned)((p.slot_stride + seg - 1) / seg));
     k_pack<<<pg, PACK_NT, 0, st>>>(d_in, g, slots, p.slot_stride, meta, calls, d_out_off, d_out, seg);
-    CK_LAUNCH();
+    CK_LAUNCH(); prof_mark(st);
     return TRC_OK;
 }
 
@@ -147,6 +172,7 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
     cudaStream_t st = (cudaStream_t)cuda_stream;
     Geom g = p.g; g.upc = 1; g.n_units = g.n_calls;     // decoders work per call
     auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
+    g_prof_n = 0; prof_mark(st);
     switch (codec) {
     case ANS4S: k_rans_static_dec<<<blocks(g.n_calls, RANS_SD_NT), RANS_SD_NT, 0, st>>>(d_in, d_in_off, d_out, g, d_cdf, cdfnum, chunks_per_cdf, flags); break;
     case RCS:   k_rc_static_dec<1><<<blocks(g.n_calls, RC_SD_NT), RC_SD_NT, 0, st>>>(d_in, d_in_off, d_out, g, d_cdf, cdfnum, chunks_per_cdf); break;
@@ -158,7 +184,7 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
         uint32_t *o1 = nullptr;
         CK(cudaMallocAsync((void **)&o1, b * AD_NT_BYTE * O1_TAB_WORDS * 4, st));
         k_rans_adapt_dec<M_O1, AD_NT_BYTE><<<(unsigned)b, AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g, o1, flags);
-        g_launches++;
+        g_launches++; prof_mark(st);
         cudaError_t e = cudaPeekAtLastError();
         cudaFreeAsync(o1, st);
         CK(e);
@@ -169,7 +195,7 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
     case RC4:   k_rc_adapt_dec<R_NIB1, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
     case RC4I:  k_rc_adapt_dec<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
     }
-    CK_LAUNCH();
+    CK_LAUNCH(); prof_mark(st);
     return TRC_OK;
 }
 
