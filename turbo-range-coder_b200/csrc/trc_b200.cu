@@ -5,6 +5,7 @@
 #include "rans_static.cuh"
 #include "rc_static.cuh"
 #include "adaptive.cuh"
+#include "static_v2.cuh"
 #include "pack.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -39,8 +40,15 @@ static inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 struct Plan {
     Geom g; int codec;
     size_t slot_stride, rec_stride, o1_threads;
-    size_t off_meta, off_calls, off_slots, off_recs, off_o1, total;
+    size_t off_meta, off_calls, off_slots, off_recs, off_o1, off_tabs, total;
 };
+
+// tables needed for n calls when `cpc` consecutive calls share one (0 = one table for everything)
+static inline size_t n_tables(size_t n_calls, size_t cpc) { return cpc ? (n_calls + cpc - 1) / cpc : 1; }
+// the throughput kernels (static_v2.cuh) need 16-byte aligned calls and table groups that do not split a CTA
+static inline bool v2_ok(const void *buf, size_t chunk_len, size_t cpc) {
+    return ((uintptr_t)buf & 15) == 0 && (chunk_len & 15) == 0 && (cpc == 0 || cpc % V2_NT == 0);
+}
 
 static int make_plan(int codec, size_t total_len, size_t chunk_len, Plan &p) {
     if (codec < 0 || codec >= NCODECS || total_len == 0 || chunk_len == 0) return TRC_E_ARG;
@@ -58,6 +66,8 @@ static int make_plan(int codec, size_t total_len, size_t chunk_len, Plan &p) {
     p.off_slots = o; o += al256(p.g.n_units * p.slot_stride);
     p.off_recs = o;  o += al256(p.g.n_units * p.rec_stride * 4);
     p.off_o1 = o;    o += al256(p.o1_threads * O1_TAB_WORDS * 4);
+    // room for one TableSet per V2_NT calls is the worst case the v2 path accepts (cpc >= V2_NT)
+    p.off_tabs = o;  o += codec_static(codec) ? al256(((p.g.n_calls + V2_NT - 1) / V2_NT) * sizeof(TableSet)) : 0;
     p.total = o;
     return TRC_OK;
 }
@@ -137,11 +147,21 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     uint32_t *o1 = (uint32_t *)(sc + p.off_o1);
     const Geom &g = p.g;
     auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
-    g_prof_n = 0; prof_mark(st);
+    g_prof_n = 0;
+    const bool v2 = codec_static(codec) && v2_ok(d_in, chunk_len, chunks_per_cdf);
+    TableSet *tabs = (TableSet *)(sc + p.off_tabs);
+    if (v2) {   // symbol tables once per launch
+        k_build_tables<<<(unsigned)n_tables(g.n_calls, chunks_per_cdf), 1024, 0, st>>>(d_cdf, cdfnum, tabs);
+        CK_LAUNCH();
+    }
+    prof_mark(st);
     switch (codec) {
-    case ANS4S: k_rans_static_enc<<<blocks(g.n_calls, RANS_S_NT), RANS_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
-    case RCS:   k_rc_static_enc<1><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
-    case RCS2:  k_rc_static_enc<2><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
+    case ANS4S: if (v2) k_rans_static_enc_v2<<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
+                else k_rans_static_enc<<<blocks(g.n_calls, RANS_S_NT), RANS_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
+    case RCS:   if (v2) k_rc_static_enc_v2<1><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
+                else k_rc_static_enc<1><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
+    case RCS2:  if (v2) k_rc_static_enc_v2<2><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
+                else k_rc_static_enc<2><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
     case ANS4:  k_rans_adapt_enc<M_NIB, AD_NT_NIB><<<blocks(g.n_units, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta); break;
     case ANS:   k_rans_adapt_enc<M_BYTE, AD_NT_BYTE><<<blocks(g.n_units, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta); break;
     case ANS1:  k_rans_adapt_enc<M_O1, AD_NT_BYTE><<<(unsigned)(p.o1_threads / AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, o1, meta); break;
@@ -172,7 +192,24 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
     cudaStream_t st = (cudaStream_t)cuda_stream;
     Geom g = p.g; g.upc = 1; g.n_units = g.n_calls;     // decoders work per call
     auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
-    g_prof_n = 0; prof_mark(st);
+    g_prof_n = 0;
+    if (codec_static(codec) && v2_ok(d_out, chunk_len, chunks_per_cdf)) {
+        TableSet *tabs = nullptr;
+        const size_t nt = n_tables(g.n_calls, chunks_per_cdf);
+        CK(cudaMallocAsync((void **)&tabs, nt * sizeof(TableSet), st));
+        k_build_tables<<<(unsigned)nt, 1024, 0, st>>>(d_cdf, cdfnum, tabs);
+        g_launches++;
+        prof_mark(st);
+        if (codec == ANS4S) k_rans_static_dec_v2<<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, chunks_per_cdf, flags);
+        else if (codec == RCS) k_rc_static_dec_v2<1><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf);
+        else k_rc_static_dec_v2<2><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf);
+        g_launches++; prof_mark(st);
+        cudaError_t e = cudaPeekAtLastError();
+        cudaFreeAsync(tabs, st);
+        CK(e);
+        return TRC_OK;
+    }
+    prof_mark(st);
     switch (codec) {
     case ANS4S: k_rans_static_dec<<<blocks(g.n_calls, RANS_SD_NT), RANS_SD_NT, 0, st>>>(d_in, d_in_off, d_out, g, d_cdf, cdfnum, chunks_per_cdf, flags); break;
     case RCS:   k_rc_static_dec<1><<<blocks(g.n_calls, RC_SD_NT), RC_SD_NT, 0, st>>>(d_in, d_in_off, d_out, g, d_cdf, cdfnum, chunks_per_cdf); break;
