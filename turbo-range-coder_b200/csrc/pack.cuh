@@ -17,41 +17,57 @@ struct CallInfo { uint32_t len; uint32_t raw; };   // raw: 0 coded, 1 raw copy o
 // Then an exclusive prefix sum over the call lengths gives the packed offsets.  Single CTA.
 constexpr int SCAN_NT = 1024;
 
-__global__ void __launch_bounds__(SCAN_NT)
-k_resolve_scan(Geom g, int blocked, UnitMeta *__restrict__ meta, CallInfo *__restrict__ calls, uint64_t *__restrict__ out_off) {
-    __shared__ uint64_t part[SCAN_NT];
-    const size_t per = (g.n_calls + SCAN_NT - 1) / SCAN_NT;
-    const size_t j0 = (size_t)threadIdx.x * per, j1 = j0 + per < g.n_calls ? j0 + per : g.n_calls;
-    uint64_t sum = 0;
-    for (size_t j = j0; j < j1; j++) {
+// step 1 (any number of CTAs, one thread per call): call length + raw flag
+__global__ void k_resolve(Geom g, int blocked, UnitMeta *__restrict__ meta, CallInfo *__restrict__ calls) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= g.n_calls) return;
+    CallInfo ci;
+    if (blocked) {
         size_t cs, N; call_span(g, j, cs, N);
-        CallInfo ci;
-        if (blocked) {
-            uint64_t o = 0; bool raw = false;
-            for (uint32_t b = 0; b < g.upc; b++) {
-                UnitMeta &m = meta[j * g.upc + b];
-                if (m.a_len == 0 && m.len == 0) break;                 // padding unit of a short last call
-                if ((m.flags & UM_OVF) || o + m.len + ((m.flags & UM_ADJ2) ? 2 : 0) >= N) { raw = true; break; }
-                m.pref = (uint32_t)o; o += m.len;
-            }
-            ci.raw = raw; ci.len = raw ? (uint32_t)N : (uint32_t)o;
-        } else {
-            const UnitMeta &m = meta[j];
-            ci.raw = (m.flags & UM_RAW) ? 1 : 0; ci.len = m.len;
+        uint64_t o = 0; bool raw = false;
+        for (uint32_t b = 0; b < g.upc; b++) {
+            UnitMeta &m = meta[j * g.upc + b];
+            if (m.a_len == 0 && m.len == 0) break;                     // padding unit of a short last call
+            if ((m.flags & UM_OVF) || o + m.len + ((m.flags & UM_ADJ2) ? 2 : 0) >= N) { raw = true; break; }
+            m.pref = (uint32_t)o; o += m.len;
         }
-        calls[j] = ci; sum += ci.len;
+        ci.raw = raw; ci.len = raw ? (uint32_t)N : (uint32_t)o;
+    } else {
+        const UnitMeta &m = meta[j];
+        ci.raw = (m.flags & UM_RAW) ? 1 : 0; ci.len = m.len;
     }
-    part[threadIdx.x] = sum;
+    calls[j] = ci;
+}
+
+// step 2 (single CTA): exclusive prefix sum of the call lengths, tile by tile with coalesced accesses
+__global__ void __launch_bounds__(SCAN_NT)
+k_scan(size_t n, const CallInfo *__restrict__ calls, uint64_t *__restrict__ out_off) {
+    __shared__ uint64_t wsum[SCAN_NT / 32];
+    __shared__ uint64_t carry_s;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (int d = 1; d < SCAN_NT; d <<= 1) {                            // Hillis-Steele inclusive scan of the partials
-        uint64_t v = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+    for (size_t base = 0; base < n; base += SCAN_NT) {
+        size_t j = base + threadIdx.x;
+        uint64_t v = j < n ? calls[j].len : 0, x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+        if (lane == 31) wsum[wid] = x;
         __syncthreads();
-        part[threadIdx.x] += v;
+        if (wid == 0) {
+            uint64_t w = wsum[lane], t = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, t, d); if (lane >= d) t += y; }
+            wsum[lane] = t - w;                                        // exclusive warp offsets
+        }
+        __syncthreads();
+        uint64_t carry = carry_s;
+        if (j < n) out_off[j] = carry + wsum[wid] + x - v;
+        __syncthreads();
+        if (threadIdx.x == SCAN_NT - 1) carry_s = carry + wsum[wid] + x;
         __syncthreads();
     }
-    uint64_t run = threadIdx.x ? part[threadIdx.x - 1] : 0;
-    for (size_t j = j0; j < j1; j++) { out_off[j] = run; run += calls[j].len; }
-    if (threadIdx.x == SCAN_NT - 1) out_off[g.n_calls] = part[SCAN_NT - 1];
+    if (threadIdx.x == 0) out_off[n] = carry_s;
 }
 
 // ---- pack ----------------------------------------------------------------------------------------------

@@ -73,6 +73,50 @@ __device__ __forceinline__ uint4 ldg128(const uint8_t *p) { return __ldg((const 
 
 constexpr int V2_NT = 128;
 
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// Same coder as RcEnc (rc_static.cuh), written so that the renormalisation is a handful of selects and one
+// predicated store instead of a branch: in a warp some lane renormalises at nearly every step, so a branch
+// would be taken (divergently) all the time and would also stop the two coders of a lane from overlapping.
+struct RcEncV2 {
+    uint64_t low, range;
+    uint8_t *base;
+    uint32_t pos, pend, carry;
+    __device__ __forceinline__ void init(uint8_t *b) { low = 0; range = ~0ull; base = b; pos = 0; pend = 0; carry = 0; }
+    __device__ __noinline__ void walk_back() {           // pending word wrapped to 0: propagate into stored words (astronomically rare)
+        uint8_t *p = base + pos - 4;
+        for (;;) { p -= 4; uint32_t w = *(uint32_t *)p + 1; *(uint32_t *)p = w; if (w) break; }
+    }
+    __device__ __forceinline__ void encode(uint32_t c0, uint32_t f) {
+        range >>= PROB_BITS;
+        uint64_t nl = low + range * c0;
+        carry |= nl < low ? 1u : 0u;
+        low = nl; range *= f;
+        const bool p = (uint32_t)(range >> 32) == 0;                                  // _rcenorm_ turborc_.h:105-109
+        const uint32_t np = pend + carry;
+        if (p && carry && np == 0 && pos >= 8) walk_back();
+        if (p && pos) *(uint32_t *)(base + pos - 4) = np;
+        pend  = p ? (uint32_t)(low >> 32) : pend;
+        pos   = p ? pos + 4 : pos;
+        carry = p ? 0u : carry;
+        low   = p ? low << 32 : low;
+        range = p ? range << 32 : range;
+    }
+    __device__ inline void put(uint32_t w) {
+        uint32_t np = pend + carry;
+        if (carry && np == 0 && pos >= 8) walk_back();
+        carry = 0;
+        if (pos) *(uint32_t *)(base + pos - 4) = np;
+        pend = w; pos += 4;
+    }
+    __device__ inline void flush() {                                                  // rceflush turborc_.h:118-128
+        if ((uint32_t)(range >> 32) == 0) { put((uint32_t)(low >> 32)); low <<= 32; range <<= 32; }
+        if (range > (1ull << 33)) { uint64_t nl = low + (1ull << 32); carry |= nl < low; low = nl; put((uint32_t)(low >> 32)); }
+        else { uint64_t nl = low + 1; carry |= nl < low; low = nl; put((uint32_t)(low >> 32)); put((uint32_t)low); }
+        *(uint32_t *)(base + pos - 4) = pend;
+    }
+};
+
 // =========================================================================================================
 // Range coder encoder, NC coders per call (rccdfsenc rccdf.c:71-82 / rccdfs2enc rccdf.c:125-143)
 // The reference evaluates its overflow test after every symbol (pair); the tested quantities only grow, so
@@ -98,7 +142,7 @@ k_rc_static_enc_v2(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const
     bool raw = false;
     const size_t nb = n & ~(size_t)15;
     if (NC == 1) {
-        RcEnc e; e.init(slot);
+        RcEncV2 e; e.init(slot);
         uint4 cur = nb ? ldg128(ip) : make_uint4(0, 0, 0, 0);
         for (size_t i = 0; i < nb && !raw; i += 16) {
             uint4 nxt = i + 32 <= nb ? ldg128(ip + i + 16) : cur;
@@ -118,7 +162,7 @@ k_rc_static_enc_v2(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const
         if (n < 4) { m.a_len = 0; m.len = (uint32_t)n; m.flags = UM_RAW; meta[j] = m; return; }
         const uint32_t b1ref = 4 + (uint32_t)(((n - 4) * 37) / 64);                  // rccdf.c:126
         const uint32_t b1 = (b1ref + 64 + 15) & ~15u;
-        RcEnc e0, e1; e0.init(slot + 4); e1.init(slot + b1);
+        RcEncV2 e0, e1; e0.init(slot + 4); e1.init(slot + b1);
         uint4 cur = nb ? ldg128(ip) : make_uint4(0, 0, 0, 0);
         for (size_t i = 0; i < nb && !raw; i += 16) {
             uint4 nxt = i + 32 <= nb ? ldg128(ip + i + 16) : cur;
@@ -154,34 +198,34 @@ k_rc_static_enc_v2(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const
 // =========================================================================================================
 struct RcDec2 {
     uint64_t range, code;
-    const uint8_t *ip, *lim;        // lim = last address a full 32-bit word can be read from
-    uint32_t nxt;                   // next stream word, already loaded
-    __device__ __forceinline__ uint32_t fetch() { uint32_t v = ip <= lim ? ld_u32(ip) : ld_u32_clamped(ip, lim + 4); ip += 4; return v; }
+    const uint32_t *ip, *lim;       // 4-byte aligned stream cursor; lim = last word that may be read
+    uint32_t n0, n1;                // the next two stream words, already loaded (hides the L2 latency of the refill)
+    __device__ __forceinline__ uint32_t fetch() { uint32_t v = ip <= lim ? __ldg(ip) : 0u; ip++; return v; }
     __device__ __forceinline__ void init(const uint8_t *p, const uint8_t *gend) {   // rcdinit turborc_.h:152-158
-        lim = gend - 4; ip = p; range = ~0ull;
+        lim = (const uint32_t *)gend - 1; ip = (const uint32_t *)p; range = ~0ull;
         uint32_t a = fetch(), b = fetch();
         code = (uint64_t)a << 32 | b;
-        nxt = fetch();
+        n0 = fetch(); n1 = fetch();
     }
     // one symbol: range >>= 15; x = max{ x : cdf[x]*range <= code } (== _cdfbget turborc_.h:307-315); _rccdfupdate
     __device__ __forceinline__ uint32_t decode(const uint8_t *lut, const uint32_t *dtab, unsigned cdfnum) {
         range >>= PROB_BITS;
-        // estimate q = code / range within +-1 (fp32: relative error < 2^-21 on a quotient < 2^16)
-        float qf = __ull2float_rz(code) * __frcp_rn(__ull2float_rn(range));
-        uint32_t q = (uint32_t)fminf(qf, 32767.0f);
+        // q ~ code / range within +-1: fp32 conversions, approximate reciprocal and product each err < 2^-22
+        // relative, the quotient is < 2^16, so the estimate is off by < 2^-5
+        float qf = __ull2float_rz(code) * rcp_approx(__ull2float_rn(range));
+        uint32_t q = min(__float2uint_rz(qf), 32767u);
         uint32_t x = lut[q], e = dtab[x];
-        uint64_t rp = (uint64_t)(e >> 16) * range;
-        if (rp > code) {                                            // estimate one too high
-            x--; e = dtab[x]; rp = (uint64_t)(e >> 16) * range;
-        } else if (x + 1 < cdfnum) {
-            uint64_t rn = rp + (uint64_t)(e & 0xffffu) * range;      // cdf[x+1] * range
-            if (rn <= code) { x++; e = dtab[x]; rp = rn; }           // estimate one too low
+        uint64_t rp = (uint64_t)(e >> 16) * range, fr = (uint64_t)(e & 0xffffu) * range;
+        if (__builtin_expect(rp > code || (rp + fr <= code && x + 1 < cdfnum), 0)) {   // exact +-1 fix-up (rare)
+            x = rp > code ? x - 1 : x + 1;
+            e = dtab[x]; rp = (uint64_t)(e >> 16) * range; fr = (uint64_t)(e & 0xffffu) * range;
         }
-        range *= (e & 0xffffu); code -= rp;
-        if ((uint32_t)(range >> 32) == 0) {                          // _rcdnorm_ turborc_.h:111
-            range <<= 32; code = code << 32 | nxt;
-            nxt = fetch();
-        }
+        code -= rp; range = fr;
+        const bool p = (uint32_t)(range >> 32) == 0;                                  // _rcdnorm_ turborc_.h:111
+        range = p ? range << 32 : range;
+        code  = p ? (code << 32 | n0) : code;
+        n0 = p ? n1 : n0;
+        if (p) n1 = fetch();
         return x;
     }
 };
@@ -228,7 +272,7 @@ k_rc_static_dec_v2(const uint8_t *__restrict__ in, const uint64_t *__restrict__ 
         for (size_t i = nb; i < n; i++) op[i] = (uint8_t)d.decode(lut, dtab, cdfnum);
     } else {
         uint32_t len0 = ld_u32_clamped(stream, gend);
-        const uint8_t *p1 = stream + 4 + len0;
+        const uint8_t *p1 = stream + 4 + (len0 & ~3u);                               // valid streams: multiple of 4
         if (p1 > gend || p1 < stream) p1 = gend;
         RcDec2 d0, d1; d0.init(stream + 4, gend); d1.init(p1, gend);
         for (size_t i = 0; i < nb; i += 16) {
@@ -247,8 +291,147 @@ k_rc_static_dec_v2(const uint8_t *__restrict__ in, const uint64_t *__restrict__ 
 }
 
 // =========================================================================================================
+// TRC_RCS2, one LANE PER CODER: lanes 2r / 2r+1 of a warp own coder 0 / coder 1 of call r, so a warp carries 32
+// independent range coders over 16 calls and the batch exposes twice as many warps to the schedulers as the
+// lane-per-call form (the coders are dependency chains: throughput comes from warps in flight).
+// The two lanes never talk inside the loop: each tests its own half of OVERFLOWI (rccdf.c:46: stream 1 against
+// the size threshold, stream 0 against the start of stream 1), both halves are monotone, and they are OR-ed once
+// at the end.
+// =========================================================================================================
+constexpr int LPC_NT = 128;                       // 64 calls per CTA
+
+__global__ void __launch_bounds__(LPC_NT)
+k_rcs2_enc_lpc(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const TableSet *__restrict__ ts, size_t cpc,
+               uint8_t *__restrict__ slots, size_t slot_stride, UnitMeta *__restrict__ meta) {
+    __shared__ __align__(16) uint32_t ctab[256];
+    __shared__ uint64_t bar;
+    const size_t j0 = (size_t)blockIdx.x * (LPC_NT / 2), j = j0 + (threadIdx.x >> 1);
+    const unsigned c = threadIdx.x & 1;
+    const TableSet *t = ts + (cpc ? j0 / cpc : 0);
+    if (threadIdx.x == 0) tma_fetch(ctab, t->ctab, sizeof ctab, &bar);
+    __syncthreads();
+    tma_wait(&bar);
+    const bool live = j < n_calls;                 // dead lanes still take part in the shuffles below
+    size_t start = 0, n = 0;
+    if (live) call_span(g, j, start, n);
+    const uint8_t *ip = in + start;
+    uint8_t *slot = slots + (live ? j : 0) * slot_stride;
+    const int64_t thr = rc_thr(n);
+    const bool tiny = n < 4;                       // reference undefined; raw
+    const uint32_t b1ref = tiny ? 4 : 4 + (uint32_t)(((n - 4) * 37) / 64);           // rccdf.c:126
+    const uint32_t b1 = (b1ref + 64 + 15) & ~15u;
+    RcEncV2 e; e.init(slot + (c ? b1 : 4));
+    bool raw = tiny || !live;
+    const size_t nb = n & ~(size_t)15;
+    uint4 cur = (nb && !raw) ? ldg128(ip) : make_uint4(0, 0, 0, 0);
+    for (size_t i = 0; i < nb && !raw; i += 16) {
+        uint4 nxt = i + 32 <= nb ? ldg128(ip + i + 16) : cur;
+        const uint32_t w[4] = { cur.x >> (8 * c), cur.y >> (8 * c), cur.z >> (8 * c), cur.w >> (8 * c) };
+        uint32_t tt[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) tt[k] = ctab[(w[k >> 1] >> (16 * (k & 1))) & 0xff];
+#pragma unroll
+        for (int k = 0; k < 8; k++) e.encode(tt[k] & 0xffffu, tt[k] >> 16);
+        raw = c ? (int64_t)b1ref + e.pos >= thr : 4 + e.pos >= b1ref;               // own half of OVERFLOWI
+        cur = nxt;
+    }
+    for (size_t i = nb + c; i < (n & ~(size_t)1) && !raw; i += 2) {                  // remaining full pairs
+        uint32_t tk = ctab[ip[i]]; e.encode(tk & 0xffffu, tk >> 16);
+        raw = c ? (int64_t)b1ref + e.pos >= thr : 4 + e.pos >= b1ref;
+    }
+    raw = __shfl_xor_sync(0xffffffffu, (int)raw, 1) || raw;                          // either half fired -> raw copy
+    if (!raw) {
+        if (c == 0 && (n & 1)) { uint32_t tk = ctab[ip[n - 1]]; e.encode(tk & 0xffffu, tk >> 16); }   // odd tail on coder 0 (rccdf.c:135-136)
+        e.flush();
+    }
+    const uint32_t mypos = e.pos, other = __shfl_xor_sync(0xffffffffu, mypos, 1);
+    if (!live || c) return;
+    const uint32_t p0 = mypos, p1 = other;
+    if (!raw) {
+        *(uint32_t *)slot = p0;                                                      // rccdf.c:141
+        if ((int64_t)(4 + p0 + p1) >= thr) raw = true;                               // rccdf.c:142
+    }
+    UnitMeta m; m.pref = 0; m.pad = 0; m.a_off = 0;
+    m.a_len = raw ? 0 : 4 + p0; m.b_off = b1; m.b_len = raw ? 0 : p1;
+    m.len = raw ? (uint32_t)n : 4 + p0 + p1; m.flags = raw ? UM_RAW : 0;
+    meta[j] = m;
+}
+
+__global__ void __launch_bounds__(LPC_NT)
+k_rcs2_dec_lpc(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint8_t *__restrict__ out, Geom g,
+               size_t n_calls, const TableSet *__restrict__ ts, unsigned cdfnum, size_t cpc) {
+    __shared__ __align__(16) uint32_t dtab[256];
+    __shared__ __align__(16) uint8_t lut[PROB_TOTAL];
+    __shared__ uint64_t bar;
+    const size_t j0 = (size_t)blockIdx.x * (LPC_NT / 2), j = j0 + (threadIdx.x >> 1);
+    const unsigned c = threadIdx.x & 1;
+    const TableSet *t = ts + (cpc ? j0 / cpc : 0);
+    if (threadIdx.x == 0) {
+        uint32_t b = smem_u32(&bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"((uint32_t)(sizeof dtab + sizeof lut)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dtab)), "l"(t->dtab), "r"((uint32_t)sizeof dtab), "r"(b) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(lut)), "l"(t->lut), "r"((uint32_t)sizeof lut), "r"(b) : "memory");
+    }
+    __syncthreads();
+    tma_wait(&bar);
+    const bool live = j < n_calls;
+    size_t start = 0, n = 0;
+    uint64_t so = 0, sl = 0;
+    if (live) { call_span(g, j, start, n); so = in_off[j]; sl = in_off[j + 1] - so; }
+    const uint8_t *gend = in + in_off[g.n_calls], *stream = in + so;
+    uint8_t *op = out + start;
+    const bool rawc = sl == n;                                                       // raw chunk: both lanes copy half
+    if (rawc || !live) {
+        if (live) { size_t h = (n / 2) & ~(size_t)15; if (c == 0) thread_copy(op, stream, h); else thread_copy(op + h, stream + h, n - h); }
+        n = 0;                                                                       // still join the shuffles
+    }
+    uint32_t len0 = n ? ld_u32_clamped(stream, gend) : 0;
+    const uint8_t *p = stream + 4 + (c ? (len0 & ~3u) : 0);                          // stream c (rccdf.c:167)
+    if (p > gend || p < stream) p = gend;
+    RcDec2 d; d.init(n ? p : gend, gend);
+    const size_t nb = n & ~(size_t)15;
+    const size_t nbmax = __reduce_max_sync(0xffffffffu, (unsigned)nb);               // warp-uniform trip count for the shuffles
+    for (size_t i = 0; i < nbmax; i += 16) {
+        uint32_t a0 = 0, a1 = 0;
+        if (i < nb) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) a0 |= d.decode(lut, dtab, cdfnum) << (8 * k);
+#pragma unroll
+            for (int k = 0; k < 4; k++) a1 |= d.decode(lut, dtab, cdfnum) << (8 * k);
+        }
+        // a0/a1 = this coder's symbols 0-3 / 4-7 of the block; interleave with the partner's
+        uint32_t b0 = __shfl_xor_sync(0xffffffffu, a0, 1), b1 = __shfl_xor_sync(0xffffffffu, a1, 1);
+        if (i < nb) {
+            uint32_t e0 = c ? b0 : a0, o0 = c ? a0 : b0, e1 = c ? b1 : a1, o1 = c ? a1 : b1;   // even-position / odd-position symbols
+            // bytes: even0 odd0 even1 odd1 | even2 odd2 even3 odd3 ...
+            uint2 v = c ? make_uint2(__byte_perm(e1, o1, 0x5140), __byte_perm(e1, o1, 0x7362))
+                        : make_uint2(__byte_perm(e0, o0, 0x5140), __byte_perm(e0, o0, 0x7362));
+            *(uint2 *)(op + i + 8 * c) = v;
+        }
+    }
+    // remaining full pairs, then the odd tail on coder 0 (rccdf.c:179-182)
+    for (size_t i = nb + c; i < (n & ~(size_t)1); i += 2) op[i] = (uint8_t)d.decode(lut, dtab, cdfnum);
+    if (c == 0 && (n & 1)) op[n - 1] = (uint8_t)d.decode(lut, dtab, cdfnum);
+}
+
+// =========================================================================================================
 // Static rANS (anscdf4senc / anscdf4sdec): both states of a call in one lane
 // =========================================================================================================
+// ece (anscdf_.h:90-94) with the renormalisation as selects + one predicated 32-bit store (see RansWriter)
+__device__ __forceinline__ uint32_t rans_enc_step_v2(uint32_t s, const uint4 e, uint8_t *base, int &pos, uint32_t &acc) {
+    const bool p = s >= e.y;
+    const int np = pos - 2;
+    const uint32_t nacc = __byte_perm(s, acc, 0x5410);
+    if (p && !(np & 2)) *(uint32_t *)(base + np) = nacc;
+    pos = p ? np : pos; acc = p ? nacc : acc; s = p ? s >> 16 : s;
+    const uint32_t q = __umulhi(s, e.x) >> (e.z >> 16);
+    return s + e.w + q * (e.z & 0xffffu);
+}
+
 __global__ void __launch_bounds__(V2_NT)
 k_rans_static_enc_v2(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const TableSet *__restrict__ ts, size_t cpc,
                      uint8_t *__restrict__ slots, size_t slot_stride, UnitMeta *__restrict__ meta) {
@@ -269,12 +452,12 @@ k_rans_static_enc_v2(const uint8_t *__restrict__ in, Geom g, size_t n_calls, con
     uint32_t i = n;
     const uint32_t n4 = n & ~3u, n16 = n & ~15u;
     bool ovf = false;
-    while (i > n4) { i--; s0 = rans_enc_step(s0, etab[ip[i]], w); }                   // tail on state 0 (anscdf.c:62-64)
+    while (i > n4) { i--; s0 = rans_enc_step_v2(s0, etab[ip[i]], w.base, w.pos, w.acc); }                   // tail on state 0 (anscdf.c:62-64)
     while (i > n16) {                                                                 // groups of 4 down to a 16-byte boundary
         i -= 4;
         uint32_t v = *(const uint32_t *)(ip + i);
-        s1 = rans_enc_step(s1, etab[v >> 24], w); s0 = rans_enc_step(s0, etab[(v >> 16) & 0xff], w);
-        s1 = rans_enc_step(s1, etab[(v >> 8) & 0xff], w); s0 = rans_enc_step(s0, etab[v & 0xff], w);
+        s1 = rans_enc_step_v2(s1, etab[v >> 24], w.base, w.pos, w.acc); s0 = rans_enc_step_v2(s0, etab[(v >> 16) & 0xff], w.base, w.pos, w.acc);
+        s1 = rans_enc_step_v2(s1, etab[(v >> 8) & 0xff], w.base, w.pos, w.acc); s0 = rans_enc_step_v2(s0, etab[v & 0xff], w.base, w.pos, w.acc);
     }
     uint4 cur = i ? ldg128(ip + i - 16) : make_uint4(0, 0, 0, 0);
     while (i > 0 && !ovf) {                                                           // anscdf.c:65-67, 16 symbols per trip
@@ -285,8 +468,8 @@ k_rans_static_enc_v2(const uint8_t *__restrict__ in, Geom g, size_t n_calls, con
         for (int k = 3; k >= 0; k--) {
             uint32_t v = wv[k];
             uint4 ea = etab[v >> 24], eb = etab[(v >> 16) & 0xff], ec = etab[(v >> 8) & 0xff], ed = etab[v & 0xff];
-            s1 = rans_enc_step(s1, ea, w); s0 = rans_enc_step(s0, eb, w);
-            s1 = rans_enc_step(s1, ec, w); s0 = rans_enc_step(s0, ed, w);
+            s1 = rans_enc_step_v2(s1, ea, w.base, w.pos, w.acc); s0 = rans_enc_step_v2(s0, eb, w.base, w.pos, w.acc);
+            s1 = rans_enc_step_v2(s1, ec, w.base, w.pos, w.acc); s0 = rans_enc_step_v2(s0, ed, w.base, w.pos, w.acc);
         }
         ovf = (uint32_t)(cap - w.pos) + 8u >= n;                                      // l >= inlen already certain
         cur = nxt;
@@ -302,17 +485,22 @@ k_rans_static_enc_v2(const uint8_t *__restrict__ in, Geom g, size_t n_calls, con
 }
 
 struct RansReader2 {
-    const uint8_t *ip, *lim;
-    uint32_t nxt;                   // next 16-bit word, already loaded
-    __device__ __forceinline__ uint32_t fetch16() { uint32_t v = ip <= lim ? ld_u16(ip) : ld_u16_clamped(ip, lim + 2); ip += 2; return v; }
+    const uint16_t *ip, *lim;       // 2-byte aligned stream cursor; lim = last halfword that may be read
+    uint32_t n0, n1;                // the next two 16-bit words, already loaded
+    __device__ __forceinline__ uint32_t fetch() { uint32_t v = ip <= lim ? (uint32_t)__ldg(ip) : 0u; ip++; return v; }
     __device__ __forceinline__ void init(const uint8_t *p, const uint8_t *gend, uint32_t &s0, uint32_t &s1) {
-        s0 = ld_u32_clamped(p, gend); s1 = ld_u32_clamped(p + 4, gend);
-        ip = p + 8; lim = gend - 2; nxt = fetch16();
+        lim = (const uint16_t *)gend - 1; ip = (const uint16_t *)p;
+        uint32_t a = fetch(), b = fetch(), c = fetch(), d = fetch();
+        s0 = a | b << 16; s1 = c | d << 16;                                           // ecdini anscdf_.h:47
+        n0 = fetch(); n1 = fetch();
     }
     __device__ __forceinline__ uint32_t step(uint32_t &s, const uint8_t *lut, const uint32_t *dtab) {
-        uint32_t r = s & PROB_MASK, x = lut[r], e = dtab[x];
+        const uint32_t r = s & PROB_MASK, x = lut[r], e = dtab[x];
         s = (e & 0xffffu) * (s >> PROB_BITS) + r - (e >> 16);                         // STATEUPD cdf_.h:37
-        if (s < ANS_L) { s = s << 16 | nxt; nxt = fetch16(); }                        // ecdnorm anscdf_.h:50-73
+        const bool p = s < ANS_L;                                                     // ecdnorm anscdf_.h:50-73
+        s = p ? (s << 16 | n0) : s;
+        n0 = p ? n1 : n0;
+        if (p) n1 = fetch();
         return x;
     }
 };

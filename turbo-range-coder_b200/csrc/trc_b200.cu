@@ -160,7 +160,7 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
                 else k_rans_static_enc<<<blocks(g.n_calls, RANS_S_NT), RANS_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
     case RCS:   if (v2) k_rc_static_enc_v2<1><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
                 else k_rc_static_enc<1><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
-    case RCS2:  if (v2) k_rc_static_enc_v2<2><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
+    case RCS2:  if (v2) k_rcs2_enc_lpc<<<blocks(g.n_calls, LPC_NT / 2), LPC_NT, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
                 else k_rc_static_enc<2><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
     case ANS4:  k_rans_adapt_enc<M_NIB, AD_NT_NIB><<<blocks(g.n_units, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta); break;
     case ANS:   k_rans_adapt_enc<M_BYTE, AD_NT_BYTE><<<blocks(g.n_units, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta); break;
@@ -171,7 +171,9 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     case RC4I:  k_rc_adapt_enc<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
     }
     CK_LAUNCH(); prof_mark(st);
-    k_resolve_scan<<<1, SCAN_NT, 0, st>>>(g, codec_blocked(codec) ? 1 : 0, meta, calls, d_out_off);
+    k_resolve<<<blocks(g.n_calls, 256), 256, 0, st>>>(g, codec_blocked(codec) ? 1 : 0, meta, calls);
+    CK_LAUNCH();
+    k_scan<<<1, SCAN_NT, 0, st>>>(g.n_calls, calls, d_out_off);
     CK_LAUNCH(); prof_mark(st);
     size_t seg = PACK_SEG_MIN;
     while ((p.slot_stride + seg - 1) / seg > 65535) seg <<= 1;
@@ -193,7 +195,16 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
     Geom g = p.g; g.upc = 1; g.n_units = g.n_calls;     // decoders work per call
     auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
     g_prof_n = 0;
-    if (codec_static(codec) && v2_ok(d_out, chunk_len, chunks_per_cdf)) {
+    if (codec_static(codec) && v2_ok(d_out, chunk_len, chunks_per_cdf) && ((uintptr_t)d_in & 3) == 0) {
+        // decode-side tables come from the stream-ordered allocator; keep its pool from trimming back to the OS
+        // at every synchronisation (the default release threshold of 0 makes each call pay a fresh cuMemMap)
+        static int s_pool_dev = -1;
+        int dev = 0; CK(cudaGetDevice(&dev));
+        if (dev != s_pool_dev) {
+            cudaMemPool_t pool; CK(cudaDeviceGetDefaultMemPool(&pool, dev));
+            unsigned long long keep = ~0ull; CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            s_pool_dev = dev;
+        }
         TableSet *tabs = nullptr;
         const size_t nt = n_tables(g.n_calls, chunks_per_cdf);
         CK(cudaMallocAsync((void **)&tabs, nt * sizeof(TableSet), st));
@@ -202,7 +213,7 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
         prof_mark(st);
         if (codec == ANS4S) k_rans_static_dec_v2<<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, chunks_per_cdf, flags);
         else if (codec == RCS) k_rc_static_dec_v2<1><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf);
-        else k_rc_static_dec_v2<2><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf);
+        else k_rcs2_dec_lpc<<<blocks(g.n_calls, LPC_NT / 2), LPC_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf);
         g_launches++; prof_mark(st);
         cudaError_t e = cudaPeekAtLastError();
         cudaFreeAsync(tabs, st);
