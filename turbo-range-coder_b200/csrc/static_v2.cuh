@@ -290,6 +290,94 @@ k_rc_static_dec_v2(const uint8_t *__restrict__ in, const uint64_t *__restrict__ 
     }
 }
 
+// ---- hand-scheduled 32-bit-halves coders for the lane-per-coder kernels ------------------------------------
+// Same arithmetic as RcEnc / RcDec (rc_static.cuh); every data-dependent event (renormalisation, carry into
+// the pending word, stream refill) is a select or a predicated memory op, never a branch.
+struct RcE32 {
+    uint32_t rl, rh, ll, lh;        // range, low
+    uint32_t pend, carry, rare;     // newest word (not stored yet), pending carry into it, "needs the slow path" flag
+    uint32_t pos;                   // words put so far
+    uint32_t *base;                 // word 0 of the stream; base[-1] must be writable scratch (first put stores a dummy there)
+    __device__ __forceinline__ void init(uint8_t *b) { rl = rh = 0xffffffffu; ll = lh = 0; pend = carry = rare = pos = 0; base = (uint32_t *)b; }
+    __device__ __forceinline__ void encode(uint32_t c0, uint32_t f) {
+        rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;                    // range >>= 15
+        const uint32_t tl = rl * c0, th = __umulhi(rl, c0) + rh * c0;                 // range * cdf[x]
+        uint32_t cy;
+        asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, 0, 0;" : "+r"(ll), "+r"(lh), "=r"(cy) : "r"(tl), "r"(th));
+        carry |= cy;                                                                  // == reference "ilow > low" at the next renorm
+        const uint32_t nl = rl * f, nh = __umulhi(rl, f) + rh * f;                    // range *= freq
+        const bool p = nh == 0;                                                       // _rcenorm_ turborc_.h:105-109
+        const uint32_t np = pend + carry;
+        rare |= (p && np < carry) ? 1u : 0u;                                          // pending word wrapped: carry must walk further back
+        if (p) base[(int)pos - 1] = np;
+        pend = p ? lh : pend; pos += p ? 1u : 0u; carry = p ? 0u : carry;
+        lh = p ? ll : lh; ll = p ? 0u : ll;
+        rh = p ? nl : nh; rl = p ? 0u : nl;
+    }
+    __device__ __forceinline__ void put(uint32_t w) {                                 // flush path only
+        const uint32_t np = pend + carry;
+        rare |= (np < carry) ? 1u : 0u;
+        base[(int)pos - 1] = np;
+        pend = w; pos++; carry = 0;
+    }
+    __device__ __forceinline__ void add_low(uint32_t al, uint32_t ah) {
+        uint32_t cy;
+        asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, 0, 0;" : "+r"(ll), "+r"(lh), "=r"(cy) : "r"(al), "r"(ah));
+        carry |= cy;
+    }
+    __device__ inline void flush() {                                                  // rceflush turborc_.h:118-128
+        if (rh == 0) { put(lh); lh = ll; ll = 0; rh = rl; rl = 0; }
+        if (rh > 2u || (rh == 2u && rl != 0)) { add_low(0, 1); put(lh); }             // range > 2^33
+        else { add_low(1, 0); put(lh); put(ll); }
+        base[(int)pos - 1] = pend;
+    }
+    __device__ __forceinline__ uint32_t bytes() const { return pos * 4; }
+};
+
+struct RcD32 {
+    uint32_t rl, rh, cl, ch;        // range, code
+    uint32_t n0, n1;                // next two stream words, already loaded
+    uint32_t wi, wlim;              // index of the next word to load; last index that may be loaded
+    const uint32_t *base;
+    __device__ __forceinline__ uint32_t fetch() { uint32_t v = wi <= wlim ? __ldg(base + wi) : 0u; wi++; return v; }
+    __device__ __forceinline__ void init(const uint8_t *p, const uint8_t *gend) {   // rcdinit turborc_.h:152-158
+        base = (const uint32_t *)p;
+        long long words = (gend - p) >> 2;
+        wi = 0; wlim = words > 0 ? (uint32_t)(words - 1) : 0u;
+        if (words <= 0) { wi = 1; wlim = 0; }                                         // nothing readable
+        rl = rh = 0xffffffffu;
+        ch = fetch(); cl = fetch(); n0 = fetch(); n1 = fetch();
+    }
+    __device__ __forceinline__ uint32_t decode(const uint8_t *lut, const uint32_t *dtab, unsigned cdfnum) {
+        rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;                    // _rccdfrange
+        // q ~ code / range within +-1 (three fp32 roundings < 2^-22 relative on a quotient < 2^16)
+        const float qf = __ull2float_rz((uint64_t)ch << 32 | cl) * rcp_approx(__ull2float_rn((uint64_t)rh << 32 | rl));
+        // floor without a float->int conversion: (min(qf, 32767) - 0.5) + 1.5*2^23 rounds to nearest and leaves the
+        // integer in the low mantissa bits (an exact-integer qf may land one low; the fix-up below covers it)
+        const uint32_t q = __float_as_uint((fminf(qf, 32767.0f) - 0.5f) + 12582912.0f) & 0xffffu;
+        uint32_t x = lut[q], e = dtab[x];
+        uint32_t c0 = e >> 16, f = e & 0xffffu;
+        uint32_t pl = rl * c0, ph = __umulhi(rl, c0) + rh * c0;                       // rp = cdf[x] * range
+        uint32_t fl = rl * f, fh = __umulhi(rl, f) + rh * f;                          // fr = freq * range
+        uint32_t dl, dh, bw;                                                          // d = code - rp, borrow => estimate too high
+        asm("sub.cc.u32 %0, %3, %5;\n\tsubc.cc.u32 %1, %4, %6;\n\tsubc.u32 %2, 0, 0;" : "=r"(dl), "=r"(dh), "=r"(bw) : "r"(cl), "r"(ch), "r"(pl), "r"(ph));
+        const bool low = dh > fh || (dh == fh && dl >= fl);                           // code - rp >= fr => estimate too low
+        if (__builtin_expect(bw != 0 || low, 0)) {                                    // exact +-1 fix-up (rare)
+            if (bw) x--; else if (x + 1 < cdfnum) x++;
+            e = dtab[x]; c0 = e >> 16; f = e & 0xffffu;
+            pl = rl * c0; ph = __umulhi(rl, c0) + rh * c0;
+            fl = rl * f; fh = __umulhi(rl, f) + rh * f;
+            asm("sub.cc.u32 %0, %2, %4;\n\tsubc.u32 %1, %3, %5;" : "=r"(dl), "=r"(dh) : "r"(cl), "r"(ch), "r"(pl), "r"(ph));
+        }
+        const bool p = fh == 0;                                                       // _rcdnorm_ turborc_.h:111
+        rh = p ? fl : fh; rl = p ? 0u : fl;
+        ch = p ? dl : dh; cl = p ? n0 : dl;
+        n0 = p ? n1 : n0;
+        if (p) n1 = fetch();
+        return x;
+    }
+};
+
 // =========================================================================================================
 // TRC_RCS2, one LANE PER CODER: lanes 2r / 2r+1 of a warp own coder 0 / coder 1 of call r, so a warp carries 32
 // independent range coders over 16 calls and the batch exposes twice as many warps to the schedulers as the
@@ -320,7 +408,7 @@ k_rcs2_enc_lpc(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const Tab
     const bool tiny = n < 4;                       // reference undefined; raw
     const uint32_t b1ref = tiny ? 4 : 4 + (uint32_t)(((n - 4) * 37) / 64);           // rccdf.c:126
     const uint32_t b1 = (b1ref + 64 + 15) & ~15u;
-    RcEncV2 e; e.init(slot + (c ? b1 : 4));
+    RcE32 e; e.init(slot + (c ? b1 : 4));
     bool raw = tiny || !live;
     const size_t nb = n & ~(size_t)15;
     uint4 cur = (nb && !raw) ? ldg128(ip) : make_uint4(0, 0, 0, 0);
@@ -332,19 +420,20 @@ k_rcs2_enc_lpc(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const Tab
         for (int k = 0; k < 8; k++) tt[k] = ctab[(w[k >> 1] >> (16 * (k & 1))) & 0xff];
 #pragma unroll
         for (int k = 0; k < 8; k++) e.encode(tt[k] & 0xffffu, tt[k] >> 16);
-        raw = c ? (int64_t)b1ref + e.pos >= thr : 4 + e.pos >= b1ref;               // own half of OVERFLOWI
+        raw = c ? (int64_t)b1ref + e.bytes() >= thr : 4 + e.bytes() >= b1ref;       // own half of OVERFLOWI
         cur = nxt;
     }
     for (size_t i = nb + c; i < (n & ~(size_t)1) && !raw; i += 2) {                  // remaining full pairs
         uint32_t tk = ctab[ip[i]]; e.encode(tk & 0xffffu, tk >> 16);
-        raw = c ? (int64_t)b1ref + e.pos >= thr : 4 + e.pos >= b1ref;
+        raw = c ? (int64_t)b1ref + e.bytes() >= thr : 4 + e.bytes() >= b1ref;
     }
     raw = __shfl_xor_sync(0xffffffffu, (int)raw, 1) || raw;                          // either half fired -> raw copy
     if (!raw) {
         if (c == 0 && (n & 1)) { uint32_t tk = ctab[ip[n - 1]]; e.encode(tk & 0xffffu, tk >> 16); }   // odd tail on coder 0 (rccdf.c:135-136)
         e.flush();
     }
-    const uint32_t mypos = e.pos, other = __shfl_xor_sync(0xffffffffu, mypos, 1);
+    const uint32_t mypos = e.bytes(), other = __shfl_xor_sync(0xffffffffu, mypos, 1);
+    const uint32_t rare = e.rare | __shfl_xor_sync(0xffffffffu, e.rare, 1);
     if (!live || c) return;
     const uint32_t p0 = mypos, p1 = other;
     if (!raw) {
@@ -352,6 +441,11 @@ k_rcs2_enc_lpc(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const Tab
         if ((int64_t)(4 + p0 + p1) >= thr) raw = true;                               // rccdf.c:142
     }
     UnitMeta m; m.pref = 0; m.pad = 0; m.a_off = 0;
+    if (rare && !raw) {   // a pending word wrapped under a carry (p ~ 2^-32 per word): redo this call with the walk-back coder
+        rc_static_enc_call<2, true>(ip, n, ctab, nullptr, slot, m);
+        meta[j] = m;
+        return;
+    }
     m.a_len = raw ? 0 : 4 + p0; m.b_off = b1; m.b_len = raw ? 0 : p1;
     m.len = raw ? (uint32_t)n : 4 + p0 + p1; m.flags = raw ? UM_RAW : 0;
     meta[j] = m;
@@ -392,7 +486,7 @@ k_rcs2_dec_lpc(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
     uint32_t len0 = n ? ld_u32_clamped(stream, gend) : 0;
     const uint8_t *p = stream + 4 + (c ? (len0 & ~3u) : 0);                          // stream c (rccdf.c:167)
     if (p > gend || p < stream) p = gend;
-    RcDec2 d; d.init(n ? p : gend, gend);
+    RcD32 d; d.init(n ? p : gend, gend);
     const size_t nb = n & ~(size_t)15;
     const size_t nbmax = __reduce_max_sync(0xffffffffu, (unsigned)nb);               // warp-uniform trip count for the shuffles
     for (size_t i = 0; i < nbmax; i += 16) {
