@@ -70,6 +70,13 @@ k_scan(size_t n, const CallInfo *__restrict__ calls, uint64_t *__restrict__ out_
     if (threadIdx.x == 0) out_off[n] = carry_s;
 }
 
+// copies the offsets of a sub-batch into host-mapped pinned memory from the SMs: a cudaMemcpy of a few KB would queue
+// on the D2H copy engine behind the multi-megabyte payload downloads of earlier sub-batches
+__global__ void k_publish_u64(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst_mapped, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst_mapped[i] = src[i];
+}
+
 // ---- pack ----------------------------------------------------------------------------------------------
 // grid = (n_units, segments); each CTA moves one `seg`-byte segment of one unit's output.
 constexpr int    PACK_NT  = 128;

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <chrono>
 
 using namespace trc;
 
@@ -287,16 +288,132 @@ struct DevBuf {
 struct Ctx {
     std::mutex mu;
     bool init = false;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, s_h2d = nullptr, s_d2h = nullptr;   // compute, upload, download
+    static constexpr int NCS = 8;
+    cudaStream_t cs[NCS];                                            // sub-batch kernels run concurrently on these
+    DevBuf sub_scratch[NCS];
     DevBuf in, out, off, cdf, scratch, status;
+    cudaEvent_t ev[2][64];                                           // [uploaded | coded] per sub-batch
+    uint64_t *h_off = nullptr, *h_off_dev = nullptr; size_t h_off_cap = 0;   // mapped pinned staging for sub-batch offsets
     int ensure() {
         if (init) return TRC_OK;
         CK(cudaSetDevice(g_dev));
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+        for (auto &x : cs) CK(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+        for (auto &row : ev) for (auto &e : row) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         init = true; return TRC_OK;
+    }
+    int need_hoff(size_t n) {
+        if (n <= h_off_cap) return TRC_OK;
+        if (h_off) cudaFreeHost(h_off);
+        h_off = nullptr; h_off_cap = 0;
+        if (cudaHostAlloc((void **)&h_off, (n + 1024) * 8, cudaHostAllocMapped) != cudaSuccess) return TRC_E_NOMEM;
+        if (cudaHostGetDevicePointer((void **)&h_off_dev, h_off, 0) != cudaSuccess) return TRC_E_CUDA;
+        h_off_cap = n + 1024; return TRC_OK;
     }
 };
 Ctx g_ctx;
+
+// Sub-batching for the host-pointer calls: upload of sub-batch i+1, coding of i and download of i-1 overlap on
+// three streams, so a host->host call costs about max(H2D, D2H) instead of their sum.  Sub-batches are whole
+// calls, aligned to table groups, ~8 MiB each, at most 64.
+constexpr size_t SUB_BYTES = 8u << 20;
+static size_t sub_calls(size_t n_calls, size_t chunk_len, size_t cpc) {
+    size_t gsz = SUB_BYTES / chunk_len;
+    if (gsz < 1) gsz = 1;
+    if (gsz * 64 < n_calls) gsz = (n_calls + 63) / 64;
+    const size_t q = cpc ? cpc : V2_NT;                              // keep table groups / CTAs whole
+    gsz = (gsz + q - 1) / q * q;
+    return gsz;
+}
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static const bool g_trace = getenv("TRC_TRACE") != nullptr;
+
+static int host_enc_pipelined(Ctx &c, int codec, const unsigned char *in, size_t total_len, size_t chunk_len, const cdf_t *cdf,
+                              unsigned cdfnum, size_t cpc, unsigned char *out, uint64_t *out_off, size_t *out_len, size_t n, size_t gsz) {
+    int rc;
+    const size_t nsub = (n + gsz - 1) / gsz, sub_len = gsz * chunk_len, stride = al256(sub_len + 512);
+    Plan p; rc = make_plan(codec, sub_len < total_len ? sub_len : total_len, chunk_len, p); if (rc) return rc;
+    if ((rc = c.in.need(total_len + 64)) || (rc = c.out.need(nsub * stride)) || (rc = c.off.need((n + nsub + 1) * 8)) ||
+        (rc = c.need_hoff(n + nsub + 1))) return rc;
+    for (auto &sb : c.sub_scratch) if ((rc = sb.need(p.total + 256))) return rc;
+    if (codec_static(codec)) {
+        if (!cdf) return TRC_E_ARG;
+        size_t nt = n_tables(n, cpc), bytes = ((nt - 1) * CDF_STRIDE + cdfnum + 1) * sizeof(cdf_t);
+        if ((rc = c.cdf.need(nt * CDF_STRIDE * sizeof(cdf_t)))) return rc;
+        CK(cudaMemcpyAsync(c.cdf.p, cdf, bytes, cudaMemcpyHostToDevice, c.s_h2d));
+    }
+    const double t_start = now_ms();
+    for (size_t i = 0; i < nsub; i++) {
+        const size_t o = i * sub_len, len = total_len - o < sub_len ? total_len - o : sub_len, calls = (len + chunk_len - 1) / chunk_len;
+        CK(cudaMemcpyAsync((uint8_t *)c.in.p + o, in + o, len, cudaMemcpyHostToDevice, c.s_h2d));
+        CK(cudaEventRecord(c.ev[0][i], c.s_h2d));
+        cudaStream_t cst = c.cs[i % Ctx::NCS];
+        DevBuf &sb = c.sub_scratch[i % Ctx::NCS];
+        CK(cudaStreamWaitEvent(cst, c.ev[0][i], 0));
+        uint64_t *doff = (uint64_t *)c.off.p + i * (gsz + 1);
+        rc = trc_enc_batch_dev(codec, (const unsigned char *)c.in.p + o, len, chunk_len,
+                               (const cdf_t *)c.cdf.p + (cpc ? (i * gsz / cpc) * CDF_STRIDE : 0), cdfnum, cpc,
+                               (unsigned char *)c.out.p + i * stride, doff, sb.p, sb.cap, cst);
+        if (rc) return rc;
+        k_publish_u64<<<(unsigned)((calls + 1 + 255) / 256), 256, 0, cst>>>(doff, c.h_off_dev + i * (gsz + 1), calls + 1);
+        CK_LAUNCH();
+        CK(cudaEventRecord(c.ev[1][i], cst));
+    }
+    uint64_t run = 0;
+    const double t_enq = now_ms();
+    if (g_trace) fprintf(stderr, "enc: enqueue took %.3f ms\n", t_enq - t_start);
+    for (size_t i = 0; i < nsub; i++) {
+        const size_t o = i * sub_len, len = total_len - o < sub_len ? total_len - o : sub_len, calls = (len + chunk_len - 1) / chunk_len;
+        CK(cudaEventSynchronize(c.ev[1][i]));
+        if (g_trace) fprintf(stderr, "  sub %zu coded at +%.3f ms\n", i, now_ms() - t_enq);
+        const uint64_t *ho = c.h_off + i * (gsz + 1);
+        const uint64_t tot = ho[calls];
+        CK(cudaMemcpyAsync(out + run, (const uint8_t *)c.out.p + i * stride, tot, cudaMemcpyDeviceToHost, c.s_d2h));
+        if (out_off) for (size_t k = 0; k < calls; k++) out_off[i * gsz + k] = run + ho[k];
+        run += tot;
+    }
+    if (out_off) out_off[n] = run;
+    CK(cudaStreamSynchronize(c.s_d2h));
+    if (g_trace) fprintf(stderr, "  enc done at +%.3f ms after enqueue end (nsub %zu)\n", now_ms() - t_enq, nsub);
+    if (out_len) *out_len = (size_t)run;
+    return TRC_OK;
+}
+
+static int host_dec_pipelined(Ctx &c, int codec, const unsigned char *in, const uint64_t *in_off, unsigned char *out, size_t total_len,
+                              size_t chunk_len, const cdf_t *cdf, unsigned cdfnum, size_t cpc, unsigned flags, size_t n, size_t gsz) {
+    int rc;
+    const size_t nsub = (n + gsz - 1) / gsz, sub_len = gsz * chunk_len;
+    const size_t in_bytes = (size_t)in_off[n];
+    if ((rc = c.in.need(in_bytes + 64)) || (rc = c.out.need(total_len + 64)) || (rc = c.off.need((n + 1) * 8))) return rc;
+    CK(cudaMemcpyAsync(c.off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, c.s_h2d));
+    if (codec_static(codec)) {
+        if (!cdf) return TRC_E_ARG;
+        size_t nt = n_tables(n, cpc), bytes = ((nt - 1) * CDF_STRIDE + cdfnum + 1) * sizeof(cdf_t);
+        if ((rc = c.cdf.need(nt * CDF_STRIDE * sizeof(cdf_t)))) return rc;
+        CK(cudaMemcpyAsync(c.cdf.p, cdf, bytes, cudaMemcpyHostToDevice, c.s_h2d));
+    }
+    for (size_t i = 0; i < nsub; i++) {
+        const size_t c0 = i * gsz, c1 = c0 + gsz < n ? c0 + gsz : n;
+        const size_t o = c0 * chunk_len, len = total_len - o < sub_len ? total_len - o : sub_len;
+        const size_t s0 = (size_t)in_off[c0], s1 = (size_t)in_off[c1];
+        CK(cudaMemcpyAsync((uint8_t *)c.in.p + s0, in + s0, s1 - s0, cudaMemcpyHostToDevice, c.s_h2d));
+        CK(cudaEventRecord(c.ev[0][i], c.s_h2d));
+        cudaStream_t cst = c.cs[i % Ctx::NCS];
+        CK(cudaStreamWaitEvent(cst, c.ev[0][i], 0));
+        rc = trc_dec_batch_dev(codec, (const unsigned char *)c.in.p, (const uint64_t *)c.off.p + c0, (unsigned char *)c.out.p + o, len, chunk_len,
+                               (const cdf_t *)c.cdf.p + (cpc ? (c0 / cpc) * CDF_STRIDE : 0), cdfnum, cpc, flags, cst);
+        if (rc) return rc;
+        CK(cudaEventRecord(c.ev[1][i], cst));
+        CK(cudaStreamWaitEvent(c.s_d2h, c.ev[1][i], 0));
+        CK(cudaMemcpyAsync(out + o, (const uint8_t *)c.out.p + o, len, cudaMemcpyDeviceToHost, c.s_d2h));
+    }
+    CK(cudaStreamSynchronize(c.s_d2h));
+    return TRC_OK;
+}
 
 int host_enc(int codec, const unsigned char *in, size_t total_len, size_t chunk_len, const cdf_t *cdf, unsigned cdfnum,
              size_t chunks_per_cdf, unsigned char *out, uint64_t *out_off, size_t *out_len) {
@@ -305,6 +422,10 @@ int host_enc(int codec, const unsigned char *in, size_t total_len, size_t chunk_
     int rc = c.ensure(); if (rc) return rc;
     Plan p; rc = make_plan(codec, total_len, chunk_len, p); if (rc) return rc;
     const size_t n = p.g.n_calls;
+    if (p.g.upc == 1 && total_len >= 4 * SUB_BYTES && chunk_len <= SUB_BYTES) {
+        const size_t gsz = sub_calls(n, chunk_len, chunks_per_cdf);
+        if (gsz < n) return host_enc_pipelined(c, codec, in, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, out, out_off, out_len, n, gsz);
+    }
     if ((rc = c.in.need(total_len + 64)) || (rc = c.out.need(trc_enc_bound(total_len, chunk_len))) ||
         (rc = c.off.need((n + 1) * 8)) || (rc = c.scratch.need(p.total + 256))) return rc;
     CK(cudaMemcpyAsync(c.in.p, in, total_len, cudaMemcpyHostToDevice, c.st));
@@ -342,6 +463,10 @@ int host_dec(int codec, const unsigned char *in, const uint64_t *in_off, size_t 
     int rc = c.ensure(); if (rc) return rc;
     Plan p; rc = make_plan(codec, total_len, chunk_len, p); if (rc) return rc;
     const size_t n = p.g.n_calls;
+    if (total_len >= 4 * SUB_BYTES && chunk_len <= SUB_BYTES && in_bytes == (size_t)in_off[n]) {
+        const size_t gsz = sub_calls(n, chunk_len, chunks_per_cdf);
+        if (gsz < n) return host_dec_pipelined(c, codec, in, in_off, out, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, flags, n, gsz);
+    }
     if ((rc = c.in.need(in_bytes + 64)) || (rc = c.out.need(total_len + 64)) || (rc = c.off.need((n + 1) * 8))) return rc;
     CK(cudaMemcpyAsync(c.off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, c.st));
     CK(cudaMemcpyAsync(c.in.p, in, in_bytes, cudaMemcpyHostToDevice, c.st));
