@@ -72,6 +72,7 @@ __device__ __forceinline__ void tma_wait(uint64_t *bar) {
 __device__ __forceinline__ uint4 ldg128(const uint8_t *p) { return __ldg((const uint4 *)p); }
 
 constexpr int V2_NT = 128;
+constexpr int LPC_NT = 128;                       // lane-per-coder kernels: 64 calls per CTA
 
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
@@ -378,6 +379,58 @@ struct RcD32 {
     }
 };
 
+// Range decoder whose stream words arrive through a per-lane ring in shared memory.
+//  * The ring (RING_W words per lane, word-major / lane-minor so any per-lane index is bank-conflict free) is
+//    topped up once per 8-symbol block with one aligned 16-byte global load; the loaded registers are only
+//    touched by the shared-memory stores at the END of the block, so the global latency hides behind the block
+//    instead of stalling the first instruction that names the register (what a register prefetch queue does).
+//  * Symbols are decoded speculatively: x = lut[~code/range] from an fp32 estimate, verified with the exact
+//    64-bit products the update needs anyway.  A failed check only sets a flag; the (rare) flagged block is
+//    re-decoded from its saved start state by the exact binary-search path, so the hot loop has no branch.
+constexpr int RING_W = 16;
+
+struct RcDRing {
+    uint32_t rl, rh, cl, ch;        // range, code
+    uint32_t n0, n1;                // next two stream words (already in registers)
+    uint32_t ci;                    // ring read cursor: absolute word index (relative to qbase) of the next word to move into n1
+    uint32_t bad;
+    __device__ __forceinline__ void step(const uint8_t *lut, const uint32_t *dtab, const uint32_t *ring, uint32_t &x_out) {
+        rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;                    // _rccdfrange
+        const float qf = __ull2float_rz((uint64_t)ch << 32 | cl) * rcp_approx(__ull2float_rn((uint64_t)rh << 32 | rl));
+        const uint32_t q = __float_as_uint((fminf(qf, 32767.0f) - 0.5f) + 12582912.0f) & 0xffffu;
+        const uint32_t x = lut[q], e = dtab[x];
+        const uint32_t c0 = e >> 16, f = e & 0xffffu;
+        const uint32_t pl = rl * c0, ph = __umulhi(rl, c0) + rh * c0;                 // rp = cdf[x] * range
+        const uint32_t fl = rl * f, fh = __umulhi(rl, f) + rh * f;                    // fr = freq * range
+        uint32_t dl, dh, bw;                                                          // d = code - rp (borrow => x too high)
+        asm("sub.cc.u32 %0, %3, %5;\n\tsubc.cc.u32 %1, %4, %6;\n\tsubc.u32 %2, 0, 0;" : "=r"(dl), "=r"(dh), "=r"(bw) : "r"(cl), "r"(ch), "r"(pl), "r"(ph));
+        bad |= bw | ((dh > fh || (dh == fh && dl >= fl)) ? 1u : 0u);                  // d >= fr => x too low
+        const bool p = fh == 0;                                                       // _rcdnorm_ turborc_.h:111
+        rh = p ? fl : fh; rl = p ? 0u : fl;
+        ch = p ? dl : dh; cl = p ? n0 : dl;
+        n0 = p ? n1 : n0;
+        if (p) n1 = ring[(ci & (RING_W - 1)) * LPC_NT];
+        ci += p ? 1u : 0u;
+        x_out = x;
+    }
+};
+
+// exact symbol step straight from global memory (redo path and tails): binary search == _cdfbget turborc_.h:307-315
+struct RcDExact {
+    uint64_t range, code;
+    const uint32_t *base; uint32_t wi, wlim;          // wi = index of the next word to read
+    __device__ __forceinline__ uint32_t fetch() { uint32_t v = wi <= wlim ? __ldg(base + wi) : 0u; wi++; return v; }
+    __device__ inline uint32_t step(const uint32_t *dtab, unsigned cdfnum) {
+        range >>= PROB_BITS;
+        unsigned x = 0, hi = cdfnum;
+        while (x + 1 < hi) { unsigned mid = (x + hi) >> 1; if ((uint64_t)(dtab[mid] >> 16) * range > code) hi = mid; else x = mid; }
+        const uint32_t e = dtab[x];
+        code -= (uint64_t)(e >> 16) * range; range *= (e & 0xffffu);
+        if ((uint32_t)(range >> 32) == 0) { range <<= 32; code = code << 32 | fetch(); }
+        return x;
+    }
+};
+
 // =========================================================================================================
 // TRC_RCS2, one LANE PER CODER: lanes 2r / 2r+1 of a warp own coder 0 / coder 1 of call r, so a warp carries 32
 // independent range coders over 16 calls and the batch exposes twice as many warps to the schedulers as the
@@ -386,7 +439,6 @@ struct RcD32 {
 // the size threshold, stream 0 against the start of stream 1), both halves are monotone, and they are OR-ed once
 // at the end.
 // =========================================================================================================
-constexpr int LPC_NT = 128;                       // 64 calls per CTA
 
 __global__ void __launch_bounds__(LPC_NT)
 k_rcs2_enc_lpc(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const TableSet *__restrict__ ts, size_t cpc,
@@ -412,8 +464,9 @@ k_rcs2_enc_lpc(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const Tab
     bool raw = tiny || !live;
     const size_t nb = n & ~(size_t)15;
     uint4 cur = (nb && !raw) ? ldg128(ip) : make_uint4(0, 0, 0, 0);
+    uint4 nxt = (nb >= 32 && !raw) ? ldg128(ip + 16) : cur;
     for (size_t i = 0; i < nb && !raw; i += 16) {
-        uint4 nxt = i + 32 <= nb ? ldg128(ip + i + 16) : cur;
+        const uint4 nxt2 = i + 48 <= nb ? ldg128(ip + i + 32) : nxt;                  // two blocks ahead: covers a DRAM miss
         const uint32_t w[4] = { cur.x >> (8 * c), cur.y >> (8 * c), cur.z >> (8 * c), cur.w >> (8 * c) };
         uint32_t tt[8];
 #pragma unroll
@@ -421,7 +474,7 @@ k_rcs2_enc_lpc(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const Tab
 #pragma unroll
         for (int k = 0; k < 8; k++) e.encode(tt[k] & 0xffffu, tt[k] >> 16);
         raw = c ? (int64_t)b1ref + e.bytes() >= thr : 4 + e.bytes() >= b1ref;       // own half of OVERFLOWI
-        cur = nxt;
+        cur = nxt; nxt = nxt2;
     }
     for (size_t i = nb + c; i < (n & ~(size_t)1) && !raw; i += 2) {                  // remaining full pairs
         uint32_t tk = ctab[ip[i]]; e.encode(tk & 0xffffu, tk >> 16);
@@ -456,6 +509,7 @@ k_rcs2_dec_lpc(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
                size_t n_calls, const TableSet *__restrict__ ts, unsigned cdfnum, size_t cpc) {
     __shared__ __align__(16) uint32_t dtab[256];
     __shared__ __align__(16) uint8_t lut[PROB_TOTAL];
+    __shared__ uint32_t ringbuf[RING_W * LPC_NT];
     __shared__ uint64_t bar;
     const size_t j0 = (size_t)blockIdx.x * (LPC_NT / 2), j = j0 + (threadIdx.x >> 1);
     const unsigned c = threadIdx.x & 1;
@@ -485,17 +539,60 @@ k_rcs2_dec_lpc(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
     }
     uint32_t len0 = n ? ld_u32_clamped(stream, gend) : 0;
     const uint8_t *p = stream + 4 + (c ? (len0 & ~3u) : 0);                          // stream c (rccdf.c:167)
-    if (p > gend || p < stream) p = gend;
-    RcD32 d; d.init(n ? p : gend, gend);
+    if (p > gend || p < stream || n == 0) p = gend;
+    // word addressing relative to the 16-byte aligned base below p
+    const uint32_t *qbase = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)15);
+    const long long wavail = ((const uint8_t *)gend - (const uint8_t *)qbase) >> 2;   // words readable from qbase (may be <= 0)
+    const uint32_t wlim = wavail > 0 ? (uint32_t)(wavail - 1) : 0u;
+    const bool none = wavail <= 0;
+    auto gword = [&](uint32_t w) -> uint32_t { return (!none && w <= wlim) ? __ldg(qbase + w) : 0u; };
+    auto gquad = [&](uint32_t w) -> uint4 {                                           // w multiple of 4
+        if (!none && w + 3 <= wlim) return __ldg((const uint4 *)(qbase + w));
+        return make_uint4(gword(w), gword(w + 1), gword(w + 2), gword(w + 3));
+    };
+    uint32_t *ring = ringbuf + threadIdx.x;
+    auto ring_put = [&](uint32_t w, const uint4 &v) {                                 // w multiple of 4
+        ring[((w + 0) & (RING_W - 1)) * LPC_NT] = v.x; ring[((w + 1) & (RING_W - 1)) * LPC_NT] = v.y;
+        ring[((w + 2) & (RING_W - 1)) * LPC_NT] = v.z; ring[((w + 3) & (RING_W - 1)) * LPC_NT] = v.w;
+    };
+    RcDRing d;
+    uint32_t fi;                                                                      // words [fi-RING_W, fi) are in the ring
+    auto resync = [&](uint32_t w0, uint64_t range, uint64_t code) {                   // (re)start the ring at word w0 = next unread word
+        fi = w0 & ~3u;
+        for (int k = 0; k < 3; k++) { ring_put(fi, gquad(fi)); fi += 4; }
+        d.rl = (uint32_t)range; d.rh = (uint32_t)(range >> 32); d.cl = (uint32_t)code; d.ch = (uint32_t)(code >> 32);
+        d.n0 = ring[(w0 & (RING_W - 1)) * LPC_NT]; d.n1 = ring[((w0 + 1) & (RING_W - 1)) * LPC_NT];
+        d.ci = w0 + 2; d.bad = 0;
+    };
+    {
+        const uint32_t w0 = (uint32_t)(((uintptr_t)p & 15) >> 2);
+        resync(w0 + 2, ~0ull, (uint64_t)gword(w0) << 32 | gword(w0 + 1));             // rcdinit turborc_.h:152-158
+    }
     const size_t nb = n & ~(size_t)15;
     const size_t nbmax = __reduce_max_sync(0xffffffffu, (unsigned)nb);               // warp-uniform trip count for the shuffles
     for (size_t i = 0; i < nbmax; i += 16) {
         uint32_t a0 = 0, a1 = 0;
         if (i < nb) {
+            const bool need = fi - d.ci <= 10;                                        // top the ring up (stores happen after the block)
+            uint4 t4 = make_uint4(0, 0, 0, 0);
+            if (need) t4 = gquad(fi);
+            const RcDRing s0 = d;                                                     // block start state (for the redo path)
+            uint32_t x;
 #pragma unroll
-            for (int k = 0; k < 4; k++) a0 |= d.decode(lut, dtab, cdfnum) << (8 * k);
+            for (int k = 0; k < 4; k++) { d.step(lut, dtab, ring, x); a0 |= x << (8 * k); }
 #pragma unroll
-            for (int k = 0; k < 4; k++) a1 |= d.decode(lut, dtab, cdfnum) << (8 * k);
+            for (int k = 0; k < 4; k++) { d.step(lut, dtab, ring, x); a1 |= x << (8 * k); }
+            const bool dry = d.ci > fi;                                               // a read ran past the filled part of the ring
+            if (need) { ring_put(fi, t4); fi += 4; }
+            if (__builtin_expect(d.bad != 0 || dry, 0)) {                             // estimate missed (or ring ran dry): exact redo
+                RcDExact ex;
+                ex.range = (uint64_t)s0.rh << 32 | s0.rl; ex.code = (uint64_t)s0.ch << 32 | s0.cl;
+                ex.base = qbase; ex.wlim = wlim; ex.wi = none ? 1u : s0.ci - 2;      // n0/n1 were words ci-2, ci-1
+                a0 = a1 = 0;
+                for (int k = 0; k < 4; k++) a0 |= ex.step(dtab, cdfnum) << (8 * k);
+                for (int k = 0; k < 4; k++) a1 |= ex.step(dtab, cdfnum) << (8 * k);
+                resync(ex.wi, ex.range, ex.code);
+            }
         }
         // a0/a1 = this coder's symbols 0-3 / 4-7 of the block; interleave with the partner's
         uint32_t b0 = __shfl_xor_sync(0xffffffffu, a0, 1), b1 = __shfl_xor_sync(0xffffffffu, a1, 1);
@@ -507,9 +604,14 @@ k_rcs2_dec_lpc(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
             *(uint2 *)(op + i + 8 * c) = v;
         }
     }
-    // remaining full pairs, then the odd tail on coder 0 (rccdf.c:179-182)
-    for (size_t i = nb + c; i < (n & ~(size_t)1); i += 2) op[i] = (uint8_t)d.decode(lut, dtab, cdfnum);
-    if (c == 0 && (n & 1)) op[n - 1] = (uint8_t)d.decode(lut, dtab, cdfnum);
+    // remaining full pairs, then the odd tail on coder 0 (rccdf.c:179-182): exact path
+    if (n > nb) {
+        RcDExact ex;
+        ex.range = (uint64_t)d.rh << 32 | d.rl; ex.code = (uint64_t)d.ch << 32 | d.cl;
+        ex.base = qbase; ex.wlim = wlim; ex.wi = none ? 1u : d.ci - 2;
+        for (size_t i = nb + c; i < (n & ~(size_t)1); i += 2) op[i] = (uint8_t)ex.step(dtab, cdfnum);
+        if (c == 0 && (n & 1)) op[n - 1] = (uint8_t)ex.step(dtab, cdfnum);
+    }
 }
 
 // =========================================================================================================

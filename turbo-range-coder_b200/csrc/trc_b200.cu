@@ -196,7 +196,7 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
     Geom g = p.g; g.upc = 1; g.n_units = g.n_calls;     // decoders work per call
     auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
     g_prof_n = 0;
-    if (codec_static(codec) && v2_ok(d_out, chunk_len, chunks_per_cdf) && ((uintptr_t)d_in & 3) == 0) {
+    if (codec_static(codec) && v2_ok(d_out, chunk_len, chunks_per_cdf) && ((uintptr_t)d_in & 15) == 0) {
         // decode-side tables come from the stream-ordered allocator; keep its pool from trimming back to the OS
         // at every synchronisation (the default release threshold of 0 makes each call pay a fresh cuMemMap)
         static int s_pool_dev = -1;
