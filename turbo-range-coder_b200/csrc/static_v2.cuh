@@ -706,6 +706,7 @@ k_rans_static_dec_v2(const uint8_t *__restrict__ in, const uint64_t *__restrict_
                      size_t n_calls, const TableSet *__restrict__ ts, size_t cpc, unsigned flags) {
     __shared__ __align__(16) uint32_t dtab[256];
     __shared__ __align__(16) uint8_t lut[PROB_TOTAL];
+    __shared__ uint32_t ringbuf[RING_W * V2_NT];
     __shared__ uint64_t bar;
     const size_t j0 = (size_t)blockIdx.x * V2_NT, j = j0 + threadIdx.x;
     const TableSet *t = ts + (cpc ? j0 / cpc : 0);
@@ -728,24 +729,64 @@ k_rans_static_dec_v2(const uint8_t *__restrict__ in, const uint64_t *__restrict_
     uint8_t *op = out + start;
     const uint32_t n = (uint32_t)len;
     if (sl == len) { thread_copy(op, in + so, len); return; }
-    RansReader2 rd; uint32_t s0, s1;
-    rd.init(in + so, gend, s0, s1);                                                   // mnfill anscdf_.h:176
-    const uint32_t n4 = n & ~3u, n16 = n & ~15u;
+    // stream halfwords arrive through a per-lane shared-memory ring (see RcDRing): hi = index of the next halfword to
+    // move into n1, relative to the 16-byte aligned base below the stream start
+    const uint8_t *p = in + so;
+    const uint32_t *qbase = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)15);
+    const long long wavail = ((const uint8_t *)gend - (const uint8_t *)qbase) >> 2;
+    const uint32_t wlim = wavail > 0 ? (uint32_t)(wavail - 1) : 0u;
+    const bool none = wavail <= 0;
+    const uint32_t hend = (uint32_t)(((const uint8_t *)gend - (const uint8_t *)qbase) >> 1);   // halfwords readable
+    auto gword = [&](uint32_t w) -> uint32_t {
+        if (!none && w <= wlim) return __ldg(qbase + w);
+        return (!none && 2 * w < hend) ? (uint32_t)__ldg((const uint16_t *)qbase + 2 * w) : 0u;   // last odd halfword
+    };
+    auto gquad = [&](uint32_t w) -> uint4 {
+        if (!none && w + 3 <= wlim) return __ldg((const uint4 *)(qbase + w));
+        return make_uint4(gword(w), gword(w + 1), gword(w + 2), gword(w + 3));
+    };
+    uint32_t *ring = ringbuf + threadIdx.x;
+    auto ring_put = [&](uint32_t w, const uint4 &v) {
+        ring[((w + 0) & (RING_W - 1)) * V2_NT] = v.x; ring[((w + 1) & (RING_W - 1)) * V2_NT] = v.y;
+        ring[((w + 2) & (RING_W - 1)) * V2_NT] = v.z; ring[((w + 3) & (RING_W - 1)) * V2_NT] = v.w;
+    };
+    auto ring_hw = [&](uint32_t h) -> uint32_t { uint32_t w = ring[((h >> 1) & (RING_W - 1)) * V2_NT]; return (h & 1) ? w >> 16 : w & 0xffffu; };
+    uint32_t hi = (uint32_t)(((uintptr_t)p & 15) >> 1);
+    uint32_t fi = 0;                                                                  // words [.., fi) are in the ring
+    for (int k = 0; k < 3; k++) { ring_put(fi, gquad(fi)); fi += 4; }
+    uint32_t s0 = ring_hw(hi) | ring_hw(hi + 1) << 16, s1 = ring_hw(hi + 2) | ring_hw(hi + 3) << 16;   // mnfill anscdf_.h:176
+    uint32_t n0 = ring_hw(hi + 4), n1 = ring_hw(hi + 5);
+    hi += 6;
+#define TRC_RSTEP(_s_, _x_) { const uint32_t r_ = _s_ & PROB_MASK, x_ = lut[r_], e_ = dtab[x_]; \
+        _s_ = (e_ & 0xffffu) * (_s_ >> PROB_BITS) + r_ - (e_ >> 16);                  /* STATEUPD cdf_.h:37 */ \
+        const bool p_ = _s_ < ANS_L;                                                  /* ecdnorm anscdf_.h:50-73 */ \
+        _s_ = p_ ? (_s_ << 16 | n0) : _s_; n0 = p_ ? n1 : n0; \
+        if (p_) { const uint32_t w_ = ring[((hi >> 1) & (RING_W - 1)) * V2_NT]; n1 = (hi & 1) ? w_ >> 16 : w_ & 0xffffu; } \
+        hi += p_ ? 1u : 0u; _x_ = x_; }
+    const uint32_t n4 = n & ~3u, n8 = n & ~7u;
     uint32_t o = 0;
-    for (; o < n16; o += 16) {                                                        // anscdf.c:82
-        uint32_t wv[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            uint32_t a = rd.step(s1, lut, dtab), b = rd.step(s0, lut, dtab), c = rd.step(s1, lut, dtab), e = rd.step(s0, lut, dtab);
-            wv[k] = a | b << 8 | c << 16 | e << 24;
-        }
-        *(uint4 *)(op + o) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    for (; o < n8; o += 8) {                                                          // anscdf.c:82, 8 symbols per ring top-up
+        const bool need = 2 * fi - hi <= 22;                                          // fewer than 12 words buffered (a block eats <= 4)
+        uint4 t4 = make_uint4(0, 0, 0, 0);
+        if (need) t4 = gquad(fi);
+        uint32_t a, b, c, e, w0, w1;
+        TRC_RSTEP(s1, a) TRC_RSTEP(s0, b) TRC_RSTEP(s1, c) TRC_RSTEP(s0, e)
+        w0 = a | b << 8 | c << 16 | e << 24;
+        TRC_RSTEP(s1, a) TRC_RSTEP(s0, b) TRC_RSTEP(s1, c) TRC_RSTEP(s0, e)
+        w1 = a | b << 8 | c << 16 | e << 24;
+        if (need) { ring_put(fi, t4); fi += 4; }
+        *(uint2 *)(op + o) = make_uint2(w0, w1);
     }
+    // tails: straight from global memory (hi-2, hi-1 are the halfwords sitting in n0, n1)
+    RansReader2 rd;
+    rd.lim = (const uint16_t *)gend - 1; rd.ip = (const uint16_t *)qbase + (hi - 2);
+    rd.n0 = rd.fetch(); rd.n1 = rd.fetch();
     for (; o < n4; o += 4) {
         uint32_t a = rd.step(s1, lut, dtab), b = rd.step(s0, lut, dtab), c = rd.step(s1, lut, dtab), e = rd.step(s0, lut, dtab);
         *(uint32_t *)(op + o) = a | b << 8 | c << 16 | e << 24;
     }
     for (; o < n; o++) op[o] = (uint8_t)((flags & 1u) ? rd.step(s0, lut, dtab) : rd.step(s1, lut, dtab));   // anscdf.c:83
+#undef TRC_RSTEP
 }
 
 }  // namespace trc
