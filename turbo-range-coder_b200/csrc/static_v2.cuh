@@ -28,21 +28,29 @@ struct __align__(16) TableSet {
 };
 static_assert(sizeof(TableSet) % 16 == 0, "bulk copies move multiples of 16 bytes");
 
+// grid = (tables, 1 + LUT_PARTS): y == 0 builds the three 256-entry tables, y >= 1 one slice of the slot->symbol LUT
+// (decoders only: `with_lut`)
+constexpr int LUT_PARTS = 8;
 __global__ void __launch_bounds__(1024)
-k_build_tables(const cdf_t *__restrict__ cdf, unsigned cdfnum, TableSet *__restrict__ ts) {
+k_build_tables(const cdf_t *__restrict__ cdf, unsigned cdfnum, TableSet *__restrict__ ts, int with_lut) {
     __shared__ uint16_t scdf[CDF_STRIDE];
     const cdf_t *c0 = cdf + (size_t)blockIdx.x * CDF_STRIDE;
     TableSet &t = ts[blockIdx.x];
+    if (blockIdx.y && !with_lut) return;
     for (unsigned x = threadIdx.x; x <= cdfnum; x += blockDim.x) scdf[x] = c0[x];
     __syncthreads();
-    for (unsigned x = threadIdx.x; x < 256; x += blockDim.x) {
-        uint32_t c = 0, f = 0;
-        if (x < cdfnum) { c = scdf[x]; f = (uint32_t)scdf[x + 1] - c; }
-        t.etab[x] = x < cdfnum ? rans_enc_entry(c, f) : make_uint4(0, 0, 0, 0);
-        t.ctab[x] = c | f << 16;
-        t.dtab[x] = (f & 0xffffu) | c << 16;
+    if (blockIdx.y == 0) {
+        for (unsigned x = threadIdx.x; x < 256; x += blockDim.x) {
+            uint32_t c = 0, f = 0;
+            if (x < cdfnum) { c = scdf[x]; f = (uint32_t)scdf[x + 1] - c; }
+            t.etab[x] = x < cdfnum ? rans_enc_entry(c, f) : make_uint4(0, 0, 0, 0);
+            t.ctab[x] = c | f << 16;
+            t.dtab[x] = (f & 0xffffu) | c << 16;
+        }
+        return;
     }
-    for (unsigned r = threadIdx.x; r < PROB_TOTAL; r += blockDim.x) {
+    const unsigned per = PROB_TOTAL / LUT_PARTS, r0 = (blockIdx.y - 1) * per;
+    for (unsigned r = r0 + threadIdx.x; r < r0 + per; r += blockDim.x) {
         unsigned x = 0, hi = cdfnum;
         while (x + 1 < hi) { unsigned mid = (x + hi) >> 1; if (scdf[mid] <= r) x = mid; else hi = mid; }
         t.lut[r] = (uint8_t)x;

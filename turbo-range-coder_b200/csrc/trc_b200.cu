@@ -152,7 +152,7 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     const bool v2 = codec_static(codec) && v2_ok(d_in, chunk_len, chunks_per_cdf);
     TableSet *tabs = (TableSet *)(sc + p.off_tabs);
     if (v2) {   // symbol tables once per launch
-        k_build_tables<<<(unsigned)n_tables(g.n_calls, chunks_per_cdf), 1024, 0, st>>>(d_cdf, cdfnum, tabs);
+        k_build_tables<<<dim3((unsigned)n_tables(g.n_calls, chunks_per_cdf), 1), 256, 0, st>>>(d_cdf, cdfnum, tabs, 0);
         CK_LAUNCH();
     }
     prof_mark(st);
@@ -209,7 +209,7 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
         TableSet *tabs = nullptr;
         const size_t nt = n_tables(g.n_calls, chunks_per_cdf);
         CK(cudaMallocAsync((void **)&tabs, nt * sizeof(TableSet), st));
-        k_build_tables<<<(unsigned)nt, 1024, 0, st>>>(d_cdf, cdfnum, tabs);
+        k_build_tables<<<dim3((unsigned)nt, 1 + LUT_PARTS), 1024, 0, st>>>(d_cdf, cdfnum, tabs, 1);
         g_launches++;
         prof_mark(st);
         if (codec == ANS4S) k_rans_static_dec_v2<<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, chunks_per_cdf, flags);
