@@ -180,22 +180,49 @@ def run_ours(args):
     clen = batch.compressed_len()
     n_chunks = batch.n
 
+    # multi-GPU: the packed streams are gathered on rank 0 inside every step.  Default: device-driven push over NVLink
+    # peer memory (shard.PeerGather) on a side stream, overlapping the decode; TRC_GATHER=nccl selects the NCCL
+    # send/recv form (shard.gather_compressed), which needs the lengths on the host and therefore a sync per step.
+    peer = None
+    gather_buf = None
+    gather_kind = "none"
+    if world > 1:
+        if os.environ.get("TRC_GATHER", "peer") == "peer":
+            try:
+                peer = shard.PeerGather(batch.out.numel(), dst=0)
+                gather_kind = "peer-memory push (CUDA IPC over NVLink), device-driven, overlapped with decode"
+            except Exception as e:                      # no peer access: fall back to NCCL
+                print(f"[rank {rank}] PeerGather unavailable ({e}); using NCCL send/recv", file=sys.stderr)
+        if peer is None:
+            gather_kind = "NCCL all-gather of lengths + grouped send/recv"
+            if rank == 0:
+                gather_buf = torch.empty(int(size * 1.05) * world, dtype=torch.uint8, device=dev)
+    side = torch.cuda.Stream(device=dev) if peer is not None else None
+    ev_enc = torch.cuda.Event(); ev_push = torch.cuda.Event()
+    total_ptr = batch.off.data_ptr() + 8 * batch.n           # device address of out_off[n] = packed length
+
     def step(ev=None):
+        main = torch.cuda.current_stream()
         flush.zero_()
         if ev: ev[0].record()
+        if peer is not None:
+            main.wait_event(ev_push)                     # previous step's push has read batch.out
         batch.encode(d_in)
-        if world > 1:
-            payload = batch.out[:clen]            # clen is fixed for the fixed input; lengths still travel every step
-            shard.gather_compressed(payload, dst=0, out=gather_buf)
+        if peer is not None:
+            ev_enc.record(main)
+            side.wait_event(ev_enc)
+            with torch.cuda.stream(side):
+                peer.push(batch.out, total_ptr, side)
+                ev_push.record(side)
+        elif world > 1:
+            shard.gather_compressed(batch.out[:clen], dst=0, out=gather_buf)
         if ev: ev[1].record()
         flush.zero_()
         if ev: ev[2].record()
         batch.decode()
+        if peer is not None and ev:
+            main.wait_event(ev_push)                     # the step ends when its stream has landed on rank 0
         if ev: ev[3].record()
-
-    gather_buf = None
-    if world > 1 and rank == 0:
-        gather_buf = torch.empty(int(size * 1.05) * world, dtype=torch.uint8, device=dev)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -219,6 +246,18 @@ def run_ours(args):
     clocks = sampler.result()
     enc_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     dec_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+    if world > 1:                                        # verify what landed on rank 0
+        dist.barrier()
+        sums = torch.zeros(world, dtype=torch.int64, device=dev)
+        sums[rank] = batch.out[:clen].to(torch.int64).sum()
+        dist.all_reduce(sums)
+        lens = torch.zeros(world, dtype=torch.int64, device=dev); lens[rank] = clen
+        dist.all_reduce(lens)
+        if rank == 0 and peer is not None:
+            got = peer.read_lens(dev)
+            assert torch.equal(got, lens), (got, lens)
+            for r in range(world):
+                assert int(peer.read_slot(r, int(lens[r]), dev).to(torch.int64).sum()) == int(sums[r]), f"gathered stream of rank {r} differs"
 
     # per-kernel durations (CUDA events between the kernels, same stream), averaged over a few extra passes
     names_enc = ["encode", "resolve_scan", "pack"]
@@ -306,7 +345,7 @@ def run_ours(args):
             "config": {"workload": f"{size} B Zipf(1.1) bytes per GPU, static CDF (cdfini on the whole buffer), batch of {chunk}-byte chunks, "
                                    f"each chunk == one reference call ({REF_FN[codec][0]}/{REF_FN[codec][1]})",
                        "codec": args.codec, "chunk_bytes": chunk, "n_chunks": n_chunks, "l2": "flushed (256 MiB write) before each timed encode and decode",
-                       "multi_gpu": "independent shard per rank, packed streams gathered on rank 0 (NCCL) inside the step" if world > 1 else "single GPU"},
+                       "multi_gpu": f"independent shard per rank, packed streams gathered on rank 0 inside the step: {gather_kind}" if world > 1 else "single GPU"},
             "enc_gbs": round(total_bytes / (enc_ms * 1e-3) / 1e9, 3), "dec_gbs": round(total_bytes / (dec_ms * 1e-3) / 1e9, 3),
             "ratio": round(clen / size, 5), "compressed_bytes": int(clen),
             "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4),

@@ -107,6 +107,17 @@ int trc_dec_batch_host(int codec, const unsigned char *in, const uint64_t *in_of
 int trc_cdfini_batch_dev(const unsigned char *d_in, size_t total_len, size_t chunk_len,
                          cdf_t *d_cdf, unsigned cdfnum, int *d_status, void *cuda_stream);
 
+/* Multi-GPU gather over peer memory (one process per GPU): the destination rank allocates a buffer, exports a
+ * CUDA-IPC handle, the other ranks open it and push their packed streams straight into it with a kernel whose byte
+ * count is read from device memory (the encoder's out_off[n]) -- no host round trip, no collective call. */
+int trc_dev_alloc(void **p, size_t bytes);
+int trc_dev_free(void *p);
+int trc_ipc_export(void *p, unsigned char *handle64);
+int trc_ipc_open(const unsigned char *handle64, void **p);
+int trc_ipc_close(void *p);
+int trc_memcpy_dev(void *dst, const void *src, size_t bytes, void *cuda_stream);
+int trc_push_dev(void *dst, const void *src, const uint64_t *d_len, size_t fixed_len, uint64_t *dst_len, void *cuda_stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Drop-in layer: the reference's names, signatures and return values.
  * ------------------------------------------------------------------------------------------------------ */

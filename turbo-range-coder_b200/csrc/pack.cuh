@@ -77,6 +77,19 @@ __global__ void k_publish_u64(const uint64_t *__restrict__ src, uint64_t *__rest
     if (i < n) dst_mapped[i] = src[i];
 }
 
+// ---- push: device-driven copy of a packed stream into (peer) memory ------------------------------------------
+// The byte count lives in device memory (it is the encoder's out_off[n]), so no host round trip is needed to size
+// the transfer.  dst may be a CUDA-IPC mapping of another GPU's buffer: the 128-bit stores then travel over
+// NVLink/NVSwitch.  Thread 0 publishes the length next to the payload.
+__global__ void __launch_bounds__(256)
+k_push(uint4 *__restrict__ dst, const uint4 *__restrict__ src, const uint64_t *__restrict__ d_len, size_t fixed_len,
+       uint64_t *__restrict__ dst_len) {
+    const uint64_t len = d_len ? *d_len : (uint64_t)fixed_len;
+    const size_t nv = (size_t)((len + 15) >> 4), stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) dst[i] = src[i];
+    if (dst_len && blockIdx.x == 0 && threadIdx.x == 0) *dst_len = len;
+}
+
 // ---- pack ----------------------------------------------------------------------------------------------
 // grid = (n_units, segments); each CTA moves one `seg`-byte segment of one unit's output.
 constexpr int    PACK_NT  = 128;

@@ -268,6 +268,31 @@ int trc_cdfini_batch_dev(const unsigned char *d_in, size_t total_len, size_t chu
     return TRC_OK;
 }
 
+// ---- peer-memory plumbing for the multi-GPU gather (shard.PeerGather) ------------------------------------------
+int trc_dev_alloc(void **p, size_t bytes) { CK(cudaMalloc(p, bytes)); CK(cudaMemset(*p, 0, bytes)); return TRC_OK; }
+int trc_dev_free(void *p) { CK(cudaFree(p)); return TRC_OK; }
+int trc_ipc_export(void *p, unsigned char *handle64) {
+    cudaIpcMemHandle_t h; CK(cudaIpcGetMemHandle(&h, p));
+    static_assert(sizeof h == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64); return TRC_OK;
+}
+int trc_ipc_open(const unsigned char *handle64, void **p) {
+    cudaIpcMemHandle_t h; memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(p, h, cudaIpcMemLazyEnablePeerAccess)); return TRC_OK;
+}
+int trc_ipc_close(void *p) { CK(cudaIpcCloseMemHandle(p)); return TRC_OK; }
+int trc_memcpy_dev(void *dst, const void *src, size_t bytes, void *cuda_stream) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream)); return TRC_OK;
+}
+// copy *d_len bytes (or fixed_len when d_len is NULL; rounded up to 16) from src to dst, publish the length at dst_len
+int trc_push_dev(void *dst, const void *src, const uint64_t *d_len, size_t fixed_len, uint64_t *dst_len, void *cuda_stream) {
+    if (!dst || !src || (((uintptr_t)dst | (uintptr_t)src) & 15)) return TRC_E_ARG;
+    static const int ctas = getenv("TRC_PUSH_CTAS") ? atoi(getenv("TRC_PUSH_CTAS")) : 32;   // few CTAs: enough stores in flight for NVLink, little SM time stolen from the coders
+    k_push<<<ctas, 256, 0, (cudaStream_t)cuda_stream>>>((uint4 *)dst, (const uint4 *)src, d_len, fixed_len, dst_len);
+    CK_LAUNCH();
+    return TRC_OK;
+}
+
 }  // extern "C"
 
 // ===========================================================================================================
