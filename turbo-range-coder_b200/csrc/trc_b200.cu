@@ -6,6 +6,7 @@
 #include "rc_static.cuh"
 #include "adaptive.cuh"
 #include "static_v2.cuh"
+#include "adaptive_coop.cuh"
 #include "pack.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -60,7 +61,7 @@ static int make_plan(int codec, size_t total_len, size_t chunk_len, Plan &p) {
     p.slot_stride = (blocked && p.g.upc > 1) ? al16(4 * (size_t)p.g.unit_max + 64) : al16(p.g.unit_max) + 192;
     p.rec_stride = blocked ? (((size_t)2 * p.g.unit_max + 3) & ~(size_t)3) + 16 : 0;
     p.o1_threads = 0;
-    if (codec == ANS1) { size_t b = (p.g.n_units + AD_NT_BYTE - 1) / AD_NT_BYTE; if (b > 32) b = 32; p.o1_threads = b * AD_NT_BYTE; }
+    // (order-1 tables live in shared memory since the warp-cooperative kernels; no global table scratch)
     size_t o = 0;
     p.off_meta = o;  o += al256(p.g.n_units * sizeof(UnitMeta));
     p.off_calls = o; o += al256(p.g.n_calls * sizeof(CallInfo));
@@ -164,8 +165,15 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     case RCS2:  if (v2) k_rcs2_enc_lpc<<<blocks(g.n_calls, LPC_NT / 2), LPC_NT, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
                 else k_rc_static_enc<2><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
     case ANS4:  k_rans_adapt_enc<M_NIB, AD_NT_NIB><<<blocks(g.n_units, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta); break;
-    case ANS:   k_rans_adapt_enc<M_BYTE, AD_NT_BYTE><<<blocks(g.n_units, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta); break;
-    case ANS1:  k_rans_adapt_enc<M_O1, AD_NT_BYTE><<<(unsigned)(p.o1_threads / AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, o1, meta); break;
+    // adaptive byte rANS: many small units -> one lane per unit (throughput); few large units -> one warp per unit (latency)
+    case ANS:   if (g.n_units >= COOP_MIN_LANE_UNITS) k_rans_adapt_enc<M_BYTE, AD_NT_BYTE><<<blocks(g.n_units, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta);
+                else k_ans_byte_enc_coop<false><<<blocks(g.n_units, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta); break;
+    case ANS1: {
+        static bool attr = false;
+        if (!attr) { CK(cudaFuncSetAttribute(k_ans_byte_enc_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)O1_SMEM_BYTES)); attr = true; }
+        k_ans_byte_enc_coop<true><<<(unsigned)(g.n_units < 148 ? g.n_units : 148), 32, O1_SMEM_BYTES, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta);
+        (void)o1; break;
+    }
     case RC:    k_rc_adapt_enc<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
     case RCI:   k_rc_adapt_enc<R_BYTE2, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
     case RC4:   k_rc_adapt_enc<R_NIB1, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
@@ -227,17 +235,13 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
     case RCS:   k_rc_static_dec<1><<<blocks(g.n_calls, RC_SD_NT), RC_SD_NT, 0, st>>>(d_in, d_in_off, d_out, g, d_cdf, cdfnum, chunks_per_cdf); break;
     case RCS2:  k_rc_static_dec<2><<<blocks(g.n_calls, RC_SD_NT), RC_SD_NT, 0, st>>>(d_in, d_in_off, d_out, g, d_cdf, cdfnum, chunks_per_cdf); break;
     case ANS4:  k_rans_adapt_dec<M_NIB, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g, nullptr, flags); break;
-    case ANS:   k_rans_adapt_dec<M_BYTE, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g, nullptr, flags); break;
+    case ANS:   if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rans_adapt_dec<M_BYTE, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g, nullptr, flags);
+                else k_ans_byte_dec_coop<false><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, d_in_off, d_out, g); break;
     case ANS1: {
-        size_t b = (g.n_calls + AD_NT_BYTE - 1) / AD_NT_BYTE; if (b > 32) b = 32;
-        uint32_t *o1 = nullptr;
-        CK(cudaMallocAsync((void **)&o1, b * AD_NT_BYTE * O1_TAB_WORDS * 4, st));
-        k_rans_adapt_dec<M_O1, AD_NT_BYTE><<<(unsigned)b, AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g, o1, flags);
-        g_launches++; prof_mark(st);
-        cudaError_t e = cudaPeekAtLastError();
-        cudaFreeAsync(o1, st);
-        CK(e);
-        return TRC_OK;
+        static bool attr = false;
+        if (!attr) { CK(cudaFuncSetAttribute(k_ans_byte_dec_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)O1_SMEM_BYTES)); attr = true; }
+        k_ans_byte_dec_coop<true><<<(unsigned)(g.n_calls < 148 ? g.n_calls : 148), 32, O1_SMEM_BYTES, st>>>(d_in, d_in_off, d_out, g);
+        break;
     }
     case RC:    k_rc_adapt_dec<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g); break;
     case RCI:   k_rc_adapt_dec<R_BYTE2, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g); break;
