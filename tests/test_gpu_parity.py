@@ -10,6 +10,7 @@ import pytest
 from helpers import CODECS, chunks, cpu_batch, first_diff
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
 
 
@@ -209,3 +210,29 @@ def test_device_api_matches_host_api(trc, port, dg):
         assert np.array_equal(off, woff) and np.array_equal(got, want)
         back = b.decode().cpu().numpy()
         assert np.array_equal(back, d)
+
+
+def test_rare_redo_paths(port, dg):
+    """TRC_FORCE_REDO=1 makes the kernels take the walk-back redo path (a pending word wrapping under a carry,
+    p ~ 2^-32 per word in real data) for every call; results must not change.  Runs in a subprocess because the hook
+    is read once at library load."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import importlib, sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        trc = importlib.import_module("turbo-range-coder_b200"); dg = importlib.import_module("turbo-range-coder_b200.datagen")
+        from oracle import cpu
+        from helpers import cpu_batch
+        port = cpu.port()
+        d = dg.bwt_shaped(150_001)
+        for codec in (trc.RC, trc.RCI):
+            for chunk in (65536, 20000):
+                want, woff = cpu_batch(port, codec, d, chunk)
+                got, off = trc.enc_batch_host(codec, d, chunk)
+                assert np.array_equal(off, woff) and np.array_equal(got, want), (codec, chunk)
+                assert np.array_equal(trc.dec_batch_host(codec, got, off, d.size, chunk), d)
+        print("redo ok")
+    ''') % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, TRC_FORCE_REDO="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "redo ok" in r.stdout, r.stdout + r.stderr

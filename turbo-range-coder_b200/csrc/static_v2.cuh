@@ -323,6 +323,34 @@ struct RcE32 {
         lh = p ? ll : lh; ll = p ? 0u : ll;
         rh = p ? nl : nh; rl = p ? 0u : nl;
     }
+    // replicated-state form (warp-cooperative kernels): every lane tracks the coder, only `writer` lanes store
+    __device__ __forceinline__ void encode_w(uint32_t c0, uint32_t f, bool writer) {
+        rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;
+        const uint32_t tl = rl * c0, th = __umulhi(rl, c0) + rh * c0;
+        uint32_t cy;
+        asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, 0, 0;" : "+r"(ll), "+r"(lh), "=r"(cy) : "r"(tl), "r"(th));
+        carry |= cy;
+        const uint32_t nl = rl * f, nh = __umulhi(rl, f) + rh * f;
+        const bool p = nh == 0;
+        const uint32_t np = pend + carry;
+        rare |= (p && np < carry) ? 1u : 0u;
+        if (p && writer) base[(int)pos - 1] = np;
+        pend = p ? lh : pend; pos += p ? 1u : 0u; carry = p ? 0u : carry;
+        lh = p ? ll : lh; ll = p ? 0u : ll;
+        rh = p ? nl : nh; rl = p ? 0u : nl;
+    }
+    __device__ __forceinline__ void put_w(uint32_t w, bool writer) {
+        const uint32_t np = pend + carry;
+        rare |= (np < carry) ? 1u : 0u;
+        if (writer) base[(int)pos - 1] = np;
+        pend = w; pos++; carry = 0;
+    }
+    __device__ inline void flush_w(bool writer) {
+        if (rh == 0) { put_w(lh, writer); lh = ll; ll = 0; rh = rl; rl = 0; }
+        if (rh > 2u || (rh == 2u && rl != 0)) { add_low(0, 1); put_w(lh, writer); }
+        else { add_low(1, 0); put_w(lh, writer); put_w(ll, writer); }
+        if (writer) base[(int)pos - 1] = pend;
+    }
     __device__ __forceinline__ void put(uint32_t w) {                                 // flush path only
         const uint32_t np = pend + carry;
         rare |= (np < carry) ? 1u : 0u;

@@ -18,6 +18,7 @@ using namespace trc;
 
 static thread_local char g_err[256] = "";
 static int g_dev = 0;
+static const int g_force_redo = getenv("TRC_FORCE_REDO") ? 1 : 0;   // test hook: exercise the rare walk-back redo paths
 static unsigned long long g_launches = 0;       // kernels launched by this library (bench.py reports the delta)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -174,8 +175,10 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
         k_ans_byte_enc_coop<true><<<(unsigned)(g.n_units < 148 ? g.n_units : 148), 32, O1_SMEM_BYTES, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta);
         (void)o1; break;
     }
-    case RC:    k_rc_adapt_enc<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
-    case RCI:   k_rc_adapt_enc<R_BYTE2, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
+    case RC:    if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_enc<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, meta);
+                else k_rc_byte_enc_coop<1><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, g, slots, p.slot_stride, meta, g_force_redo); break;
+    case RCI:   if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_enc<R_BYTE2, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, meta);
+                else k_rc_byte_enc_coop<2><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, g, slots, p.slot_stride, meta, g_force_redo); break;
     case RC4:   k_rc_adapt_enc<R_NIB1, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
     case RC4I:  k_rc_adapt_enc<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
     }
@@ -243,8 +246,10 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
         k_ans_byte_dec_coop<true><<<(unsigned)(g.n_calls < 148 ? g.n_calls : 148), 32, O1_SMEM_BYTES, st>>>(d_in, d_in_off, d_out, g);
         break;
     }
-    case RC:    k_rc_adapt_dec<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g); break;
-    case RCI:   k_rc_adapt_dec<R_BYTE2, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g); break;
+    case RC:    if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_dec<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g);
+                else k_rc_byte_dec_coop<1><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, d_in_off, d_out, g); break;
+    case RCI:   if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_dec<R_BYTE2, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g);
+                else k_rc_byte_dec_coop<2><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, d_in_off, d_out, g); break;
     case RC4:   k_rc_adapt_dec<R_NIB1, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
     case RC4I:  k_rc_adapt_dec<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
     }
