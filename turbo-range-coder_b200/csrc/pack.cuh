@@ -39,7 +39,10 @@ __global__ void k_resolve(Geom g, int blocked, UnitMeta *__restrict__ meta, Call
     calls[j] = ci;
 }
 
-// step 2 (single CTA): exclusive prefix sum of the call lengths, tile by tile with coalesced accesses
+// step 2 (single CTA): exclusive prefix sum of the call lengths.  Each thread owns SCAN_PER consecutive calls of a
+// SCAN_NT*SCAN_PER tile: its loads are issued together (one memory round trip per tile), the block-wide part is two
+// shuffle scans, and its SCAN_PER offsets leave as 128-bit stores.
+constexpr int SCAN_PER = 8;
 __global__ void __launch_bounds__(SCAN_NT)
 k_scan(size_t n, const CallInfo *__restrict__ calls, uint64_t *__restrict__ out_off) {
     __shared__ uint64_t wsum[SCAN_NT / 32];
@@ -47,9 +50,21 @@ k_scan(size_t n, const CallInfo *__restrict__ calls, uint64_t *__restrict__ out_
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    for (size_t base = 0; base < n; base += SCAN_NT) {
-        size_t j = base + threadIdx.x;
-        uint64_t v = j < n ? calls[j].len : 0, x = v;
+    for (size_t base = 0; base < n; base += (size_t)SCAN_NT * SCAN_PER) {
+        const size_t j0 = base + (size_t)threadIdx.x * SCAN_PER;
+        uint32_t v[SCAN_PER];
+        if (j0 + SCAN_PER <= n) {
+            const uint4 *p = (const uint4 *)(calls + j0);                   // 2 CallInfo per uint4 (calls is 256-byte aligned)
+#pragma unroll
+            for (int k = 0; k < SCAN_PER / 2; k++) { uint4 q = p[k]; v[2 * k] = q.x; v[2 * k + 1] = q.z; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_PER; k++) v[k] = j0 + k < n ? calls[j0 + k].len : 0u;
+        }
+        uint64_t tot = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_PER; k++) tot += v[k];
+        uint64_t x = tot;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
         if (lane == 31) wsum[wid] = x;
@@ -58,11 +73,22 @@ k_scan(size_t n, const CallInfo *__restrict__ calls, uint64_t *__restrict__ out_
             uint64_t w = wsum[lane], t = w;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { uint64_t y = __shfl_up_sync(0xffffffffu, t, d); if (lane >= d) t += y; }
-            wsum[lane] = t - w;                                        // exclusive warp offsets
+            wsum[lane] = t - w;                                             // exclusive warp offsets
         }
         __syncthreads();
-        uint64_t carry = carry_s;
-        if (j < n) out_off[j] = carry + wsum[wid] + x - v;
+        const uint64_t carry = carry_s;
+        uint64_t run = carry + wsum[wid] + x - tot;                         // exclusive offset of this thread's first call
+        if (j0 + SCAN_PER <= n && ((uintptr_t)(out_off + j0) & 15) == 0) {
+            uint64_t o[SCAN_PER];
+#pragma unroll
+            for (int k = 0; k < SCAN_PER; k++) { o[k] = run; run += v[k]; }
+            ulonglong2 *d = (ulonglong2 *)(out_off + j0);
+#pragma unroll
+            for (int k = 0; k < SCAN_PER / 2; k++) d[k] = make_ulonglong2(o[2 * k], o[2 * k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_PER; k++) { if (j0 + k < n) out_off[j0 + k] = run; run += v[k]; }
+        }
         __syncthreads();
         if (threadIdx.x == SCAN_NT - 1) carry_s = carry + wsum[wid] + x;
         __syncthreads();
@@ -133,6 +159,36 @@ k_pack(const uint8_t *__restrict__ in, Geom g, const uint8_t *__restrict__ slots
         size_t s = seg0 > m.a_len ? seg0 : m.a_len;
         group_copy(dst + s, slot + m.b_off + (s - m.a_len), seg1 - s, threadIdx.x, PACK_NT);
     }
+}
+
+// small units (one segment each): a warp per unit, 8 units per CTA -- the per-CTA launch cost of the general kernel
+// would dominate a 3 KB copy
+constexpr int PACKS_WARPS = 8;
+__global__ void __launch_bounds__(PACKS_WARPS * 32)
+k_pack_small(const uint8_t *__restrict__ in, Geom g, const uint8_t *__restrict__ slots, size_t slot_stride,
+             const UnitMeta *__restrict__ meta, const CallInfo *__restrict__ calls, const uint64_t *__restrict__ out_off,
+             uint8_t *__restrict__ out) {
+    const unsigned lane = threadIdx.x & 31;
+    const size_t u = (size_t)blockIdx.x * PACKS_WARPS + (threadIdx.x >> 5);
+    if (u >= g.n_units) return;
+    size_t j, start, len; uint32_t b;
+    unit_span(g, u, j, b, start, len);
+    if (len == 0) return;
+    const CallInfo ci = calls[j];
+    if (ci.raw) {
+        size_t cs = j * g.chunk, uo = start - cs;
+        if (uo >= ci.len) return;
+        size_t n = ci.len - uo < len ? ci.len - uo : len;
+        size_t ccs, N; call_span(g, j, ccs, N);
+        if (ci.len > N && b == 0 && lane == 0) for (size_t k = N; k < ci.len; k++) out[out_off[j] + k] = 0;   // rccdf4ienc quirk
+        group_copy(out + out_off[j] + uo, in + start, n, lane, 32);
+        return;
+    }
+    const UnitMeta m = meta[u];
+    uint8_t *dst = out + out_off[j] + m.pref;
+    const uint8_t *slot = slots + u * slot_stride;
+    if (m.a_len) group_copy(dst, slot + m.a_off, m.a_len, lane, 32);
+    if (m.b_len) group_copy(dst + m.a_len, slot + m.b_off, m.b_len, lane, 32);
 }
 
 // ---- cdfini --------------------------------------------------------------------------------------------

@@ -190,7 +190,8 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     size_t seg = PACK_SEG_MIN;
     while ((p.slot_stride + seg - 1) / seg > 65535) seg <<= 1;
     dim3 pg((unsigned)g.n_units, (unsigned)((p.slot_stride + seg - 1) / seg));
-    k_pack<<<pg, PACK_NT, 0, st>>>(d_in, g, slots, p.slot_stride, meta, calls, d_out_off, d_out, seg);
+    if (pg.y == 1) k_pack_small<<<blocks(g.n_units, PACKS_WARPS), PACKS_WARPS * 32, 0, st>>>(d_in, g, slots, p.slot_stride, meta, calls, d_out_off, d_out);
+    else k_pack<<<pg, PACK_NT, 0, st>>>(d_in, g, slots, p.slot_stride, meta, calls, d_out_off, d_out, seg);
     CK_LAUNCH(); prof_mark(st);
     return TRC_OK;
 }

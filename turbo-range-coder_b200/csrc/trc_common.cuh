@@ -123,6 +123,33 @@ __device__ inline void thread_copy(uint8_t *dst, const uint8_t *src, size_t n) {
 // funnel-shifted into place.  `tid`/`nthr` = the cooperating threads.  Reads at most the aligned word that
 // holds the last source byte.
 __device__ inline void group_copy(uint8_t *dst, const uint8_t *src, size_t n, unsigned tid, unsigned nthr) {
+    if (((((uintptr_t)dst | (uintptr_t)src) & 3) == 0) && n >= 64) {
+        // both sides word aligned (every range-coder piece): 128-bit stores on the destination's 16-byte grid, source
+        // words taken from two aligned 128-bit loads and rotated by the (uniform) word misalignment
+        size_t headw = ((16 - ((uintptr_t)dst & 15)) & 15) >> 2;                // words until dst is 16-byte aligned
+        if (tid < headw) ((uint32_t *)dst)[tid] = ((const uint32_t *)src)[tid];
+        const uint32_t *s = (const uint32_t *)src + headw;
+        uint4 *d16 = (uint4 *)((uint32_t *)dst + headw);
+        const size_t nw = (n >> 2) - headw, nv = nw >> 2;
+        const unsigned mis = (unsigned)(((uintptr_t)s & 15) >> 2);
+        const uint4 *s16 = (const uint4 *)((uintptr_t)s & ~(uintptr_t)15);
+        for (size_t i = tid; i < nv; i += nthr) {
+            uint4 lo = s16[i], v;
+            if (mis == 0) v = lo;
+            else {
+                uint4 hi = s16[i + 1];
+                if (mis == 1) v = make_uint4(lo.y, lo.z, lo.w, hi.x);
+                else if (mis == 2) v = make_uint4(lo.z, lo.w, hi.x, hi.y);
+                else v = make_uint4(lo.w, hi.x, hi.y, hi.z);
+            }
+            d16[i] = v;
+        }
+        const size_t donew = headw + (nv << 2), totw = n >> 2;
+        if (donew + tid < totw) ((uint32_t *)dst)[donew + tid] = ((const uint32_t *)src)[donew + tid];   // < 4 tail words
+        const size_t doneb = totw << 2;
+        if (tid < n - doneb) dst[doneb + tid] = src[doneb + tid];
+        return;
+    }
     size_t head = (4 - ((uintptr_t)dst & 3)) & 3;
     if (head > n) head = n;
     if (tid < head) dst[tid] = src[tid];
