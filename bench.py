@@ -34,11 +34,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CODECS = {"ans4s": 0, "ans4": 1, "ans": 2, "ans1": 3, "rcs": 4, "rcs2": 5, "rc": 6, "rci": 7, "rc4": 8, "rc4i": 9}
+CODECS = {"ans4s": 0, "ans4": 1, "ans": 2, "ans1": 3, "rcs": 4, "rcs2": 5, "rc": 6, "rci": 7, "rc4": 8, "rc4i": 9, "answ": 10}
 REF_FN = {0: ("anscdf4senc", "anscdf4sdec"), 1: ("anscdf4enc", "anscdf4dec"), 2: ("anscdfenc", "anscdfdec"),
           3: ("anscdf1enc", "anscdf1dec"), 4: ("rccdfsenc", "rccdfsbdec"), 5: ("rccdfs2enc", "rccdfsb2dec"),
           6: ("rccdfenc", "rccdfdec"), 7: ("rccdfienc", "rccdfidec"), 8: ("rccdf4enc", "rccdf4dec"),
-          9: ("rccdf4ienc", "rccdf4idec")}
+          9: ("rccdf4ienc", "rccdf4idec"),
+          10: ("answenc", "answdec")}       # this repository's 32-way interleaved static rANS: no reference function, CPU leg = oracle port
 METRIC = "encode+decode GB/s on 100MB order-0 byte stream; bitstream bit-exact vs ref"
 
 
@@ -101,7 +102,7 @@ def cpu_reference_run(codec, data, cdf, threads, reps, sample_bytes):
     from oracle import cpu
     enc, dec = REF_FN[codec]
     sample = data[:sample_bytes]
-    r = cpu.cpu_bench(True, enc, dec, sample, 4 << 20, cdf if codec in (0, 4, 5) else None, 256 if codec in (4, 5) else 0,
+    r = cpu.cpu_bench(codec != 10, enc, dec, sample, 4 << 20, cdf if codec in (0, 4, 5, 10) else None, 256 if codec in (4, 5, 10) else 0,
                       threads=threads, reps=reps)
     r["sample_bytes"] = int(sample.size)
     return r
@@ -159,10 +160,10 @@ def run_ours(args):
     trc.lib.trc_set_device(local)
     codec = CODECS[args.codec]
     size, chunk = args.size, args.chunk
-    static = codec in (0, 4, 5)
+    static = codec in (0, 4, 5, 10)
 
     data = make_data(size, rank)
-    if codec in (0, 1, 8, 9) and not (codec == 0 and args.bytes_alphabet):
+    if codec in (0, 1, 8, 9) and not (codec == 0 and args.bytes_alphabet):   # 16-symbol codecs get the low nibbles
         data = data & 15
     d_in = torch.from_numpy(data).to(dev)
     batch = trc.DeviceBatch(codec, size, chunk, cdfnum=(256 if static else 0), device=dev)

@@ -41,7 +41,10 @@ enum trc_codec {
     TRC_RCI   = 7,  /* [R10]   rccdfienc   / rccdfidec    adaptive byte RC, 2 coders       rccdf.c:213-249  */
     TRC_RC4   = 8,  /* [R11]   rccdf4enc   / rccdf4dec    adaptive nibble RC               rccdf.c:251-278  */
     TRC_RC4I  = 9,  /* [R11]   rccdf4ienc  / rccdf4idec   adaptive nibble RC, 2 coders     rccdf.c:280-323  */
-    TRC_NCODECS = 10
+    TRC_ANSW  = 10, /* NOT a reference format: 32-way warp-interleaved static rANS, one state per lane, one stream per call
+                       (the layout BASELINE's north star describes).  Parity unpinned: oracle/trc_oracle.c orc_answenc/dec is
+                       the specification.  Static table like TRC_ANS4S; chunk_len must be a multiple of 4. */
+    TRC_NCODECS = 11
 };
 
 #define TRC_CDF_STRIDE 257                    /* entries per static table (cdf_t cdf[0x100+1], turborc.c:423) */

@@ -27,6 +27,7 @@ ENCODERS = {
     "anscdf1enc": (False, False), "rccdfsenc": (True, True), "rccdfs2enc": (True, True),
     "rccdfenc": (False, False), "rccdfienc": (False, False), "rccdf4enc": (False, False),
     "rccdf4ienc": (False, False),
+    "answenc": (True, True),      # port-only: this repository's 32-way interleaved static rANS (parity unpinned)
 }
 DECODERS = {
     "anscdf4sdec": (True, False), "anscdf4dec": (False, False), "anscdfdec": (False, False),
@@ -35,7 +36,7 @@ DECODERS = {
     "rccdfdec": (False, False), "rccdfidec": (False, False), "rccdf4dec": (False, False),
     "rccdf4idec": (False, False),
     # port-only (no reference counterpart): true inverses with the tail state fixed / wide alphabet
-    "ans_sdec_n": (True, True), "anscdf4dec_fix": (False, False),
+    "ans_sdec_n": (True, True), "anscdf4dec_fix": (False, False), "answdec": (True, True),
 }
 PAIRS = {  # encoder -> decoder the reference harness pairs it with (turborc.c:495-536)
     "anscdf4senc": "anscdf4sdec", "anscdf4enc": "anscdf4dec", "anscdfenc": "anscdfdec",

@@ -541,3 +541,63 @@ size_t orc_rccdf4idec(const uint8_t *in, size_t outlen, uint8_t *out) {         
     for (; i < outlen; i++) out[i] = (uint8_t)rcd_nib(&d0, t);
     return outlen;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * TRC_ANSW: 32-way interleaved static rANS, a NEW stream format of this repository (SURVEY.md
+ * section 8c "wide static byte rANS").  PARITY UNPINNED: no reference codec produces or reads
+ * this layout, so this restatement is the format's specification, not a reference check; the
+ * per-symbol arithmetic is the reference's (ece anscdf_.h:90-94, STATEUPD cdf_.h:37, ecdnorm
+ * anscdf_.h:50-73, 15-bit CDF, 16-bit words).  Acceptance = exact round trip + size bound.
+ *
+ * Layout of one call: [32 x u32 states, state 0 first][u16 words ...].  Symbol i belongs to state
+ * (i / 4) % 32: a 128-symbol super-group gives each state 4 consecutive symbols (one 32-bit word
+ * per GPU lane).  Decoder: for every super-group, for k = 0..3: each state decodes symbol
+ * 128g + 4s + k (if < n); then the states that dropped below 2^15 refill one word each, in
+ * increasing state order.  The encoder runs the exact reverse and writes words downwards.
+ * Raw rule: a stream that is not shorter than the input is replaced by a raw copy (length == n).
+ * ------------------------------------------------------------------------------------------ */
+size_t orc_answenc(const uint8_t *in, size_t n, uint8_t *out, const cdf_t *cdf, unsigned cdfnum) {
+    (void)cdfnum;
+    size_t cap = 2 * n + 256;
+    uint8_t *buf = (uint8_t *)malloc(cap), *ep = buf + cap;
+    uint32_t st[32];
+    for (int s = 0; s < 32; s++) st[s] = ANS_L;
+    size_t ng = (n + 127) / 128;
+    for (size_t g = ng; g-- > 0;)
+        for (int k = 3; k >= 0; k--)
+            for (int s = 31; s >= 0; s--) {                    /* words of one step end up in increasing state order */
+                size_t i = g * 128 + (size_t)s * 4 + (size_t)k;
+                if (i >= n) continue;
+                unsigned x = in[i];
+                st[s] = rans_put(st[s], cdf[x], cdf[x + 1] - cdf[x], &ep);
+            }
+    for (int s = 31; s >= 0; s--) { ep -= 4; st32(ep, st[s]); }
+    size_t l = (size_t)(buf + cap - ep);
+    if (l >= n) { memcpy(out, in, n); l = n; } else memcpy(out, ep, l);
+    free(buf);
+    return l;
+}
+
+size_t orc_answdec(const uint8_t *in, size_t n, uint8_t *out, const cdf_t *cdf, unsigned cdfnum) {
+    const uint8_t *ip = in;
+    uint32_t st[32];
+    for (int s = 0; s < 32; s++) { st[s] = ld32(ip); ip += 4; }
+    size_t ng = (n + 127) / 128;
+    for (size_t g = 0; g < ng; g++)
+        for (int k = 0; k < 4; k++) {
+            for (int s = 0; s < 32; s++) {
+                size_t i = g * 128 + (size_t)s * 4 + (size_t)k;
+                if (i >= n) continue;
+                uint32_t r = st[s] & (PROB_TOTAL - 1); unsigned x = 0;
+                while (x + 1 < cdfnum && cdf[x + 1] <= r) x++;
+                st[s] = rans_get(st[s], cdf[x], cdf[x + 1]);
+                out[i] = (uint8_t)x;
+            }
+            for (int s = 0; s < 32; s++) {
+                size_t i = g * 128 + (size_t)s * 4 + (size_t)k;
+                if (i >= n) continue;
+                st[s] = rans_refill(st[s], &ip);
+            }
+        }
+    return n;
+}

@@ -236,3 +236,57 @@ def test_rare_redo_paths(port, dg):
     env = dict(os.environ, TRC_FORCE_REDO="1")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "redo ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_randomized_geometries(trc, port, dg):
+    """Seeded random (codec, source, length, chunk length) cases incl. degenerate ones (1-byte chunks, chunk > data,
+    lengths around the 16/32-byte kernel block sizes)."""
+    rng = np.random.default_rng(20261017)
+    srcs = [dg.zipf(400_000, seed=21), dg.bwt_shaped(400_000, seed=22), dg.markov1(400_000, seed=23), dg.uniform(400_000, seed=24),
+            np.zeros(400_000, np.uint8), (np.arange(400_000) % 251).astype(np.uint8)]
+    for case in range(200):
+        codec = int(rng.integers(0, 10))
+        src = srcs[int(rng.integers(0, len(srcs)))]
+        n = int(rng.choice([1, 2, 3, 5, 15, 16, 17, 31, 32, 33, 47, 63, 64, 65, 127, 129, 255, 1000, 4097, 20_001, int(rng.integers(1, 400_000))]))
+        chunk = int(rng.choice([1, 2, 3, 4, 7, 16, 32, 48, 100, 256, 1024, 4096, 4100, 65536, n, n + 5, int(rng.integers(1, 70_000))]))
+        if n // max(chunk, 1) > 60_000:          # keep the oracle loop short
+            chunk = max(chunk, n // 50_000 + 1)
+        off0 = int(rng.integers(0, 400_000 - n + 1))
+        d = np.ascontiguousarray(src[off0:off0 + n])
+        if CODECS[codec][3]:
+            d = dg.nibbles(d)
+        if CODECS[codec][2]:
+            try:
+                port.cdfini(d)
+            except ValueError:                    # degenerate table: the reference die()s
+                continue
+        _check_batch(trc, port, codec, d, chunk, f"case{case}/n{n}/chunk{chunk}")
+
+
+def test_wide_rans_answ(trc, port, dg):
+    """TRC_ANSW, the 32-way warp-interleaved static rANS (a NEW format, parity unpinned): GPU bytes == the format
+    specification in oracle/trc_oracle.c, exact round trip, and size within 4*32 bytes + 0.01 % of the static range
+    coder's on the same table (SURVEY.md section 8c acceptance)."""
+    for sname, n, chunk in [("zipf", 300_000, 4096), ("zipf", 300_000, 65536), ("bwt", 100_003, 16384), ("zipf", 1000, 1000),
+                            ("uniform", 50_000, 4096), ("zipf", 129, 128), ("zipf", 5, 4), ("o1", 262_144 + 77, 262_144)]:
+        d = {"zipf": dg.zipf, "bwt": dg.bwt_shaped, "uniform": dg.uniform, "o1": dg.markov1}[sname](n)
+        cdf = port.cdfini(d)
+        parts, offs = [], [0]
+        for s in range(0, n, chunk):
+            r, o = port.enc("answenc", d[s:s + chunk], cdf, 256)
+            parts.append(o); offs.append(offs[-1] + r)
+        want, woff = np.concatenate(parts), np.array(offs, np.uint64)
+        got, goff = trc.enc_batch_host(trc.ANSW, d, chunk, cdf=cdf, cdfnum=256)
+        assert np.array_equal(goff, woff), (sname, n, chunk, first_diff(goff, woff))
+        assert np.array_equal(got, want), (sname, n, chunk, first_diff(got, want))
+        back = trc.dec_batch_host(trc.ANSW, got, goff, n, chunk, cdf=cdf, cdfnum=256)
+        assert np.array_equal(back, d), (sname, n, chunk, first_diff(back, d))
+    d = dg.zipf(4_000_000)
+    cdf = port.cdfini(d)
+    got, goff = trc.enc_batch_host(trc.ANSW, d, 65536, cdf=cdf, cdfnum=256)
+    rc_len = port.enc("rccdfsenc", d, cdf, 256)[0]
+    n_chunks = trc.num_chunks(d.size, 65536)
+    assert int(goff[-1]) <= rc_len * 1.0001 + n_chunks * 4 * 32, (int(goff[-1]), rc_len)
+    assert np.array_equal(trc.dec_batch_host(trc.ANSW, got, goff, d.size, 65536, cdf=cdf, cdfnum=256), d)
+    with pytest.raises(trc.TrcError):                      # our own format: calls must start 4-byte aligned
+        trc.enc_batch_host(trc.ANSW, d[:10_000], 1001, cdf=cdf, cdfnum=256)

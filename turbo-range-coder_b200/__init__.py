@@ -17,8 +17,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtrc_b200.so")
 
 # enum trc_codec (include/trc_b200.h)
-ANS4S, ANS4, ANS, ANS1, RCS, RCS2, RC, RCI, RC4, RC4I = range(10)
-CODEC_NAMES = ["ANS4S", "ANS4", "ANS", "ANS1", "RCS", "RCS2", "RC", "RCI", "RC4", "RC4I"]
+ANS4S, ANS4, ANS, ANS1, RCS, RCS2, RC, RCI, RC4, RC4I, ANSW = range(11)
+CODEC_NAMES = ["ANS4S", "ANS4", "ANS", "ANS1", "RCS", "RCS2", "RC", "RCI", "RC4", "RC4I", "ANSW"]
 #: codec id -> (reference encoder, reference decoder)
 REF_NAMES = {
     ANS4S: ("anscdf4senc", "anscdf4sdec"), ANS4: ("anscdf4enc", "anscdf4dec"), ANS: ("anscdfenc", "anscdfdec"),
@@ -26,7 +26,7 @@ REF_NAMES = {
     RC: ("rccdfenc", "rccdfdec"), RCI: ("rccdfienc", "rccdfidec"), RC4: ("rccdf4enc", "rccdf4dec"),
     RC4I: ("rccdf4ienc", "rccdf4idec"),
 }
-STATIC = (ANS4S, RCS, RCS2)
+STATIC = (ANS4S, RCS, RCS2, ANSW)
 F_REF_TAIL = 1
 CDF_STRIDE = 257
 OK, E_ARG, E_CUDA, E_NOMEM = 0, -1, -2, -3

@@ -7,6 +7,7 @@
 #include "adaptive.cuh"
 #include "static_v2.cuh"
 #include "adaptive_coop.cuh"
+#include "rans_wide.cuh"
 #include "pack.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -59,7 +60,8 @@ static int make_plan(int codec, size_t total_len, size_t chunk_len, Plan &p) {
     p.codec = codec;
     p.g = make_geom(codec, total_len, chunk_len);
     const bool blocked = codec_blocked(codec);
-    p.slot_stride = (blocked && p.g.upc > 1) ? al16(4 * (size_t)p.g.unit_max + 64) : al16(p.g.unit_max) + 192;
+    p.slot_stride = (blocked && p.g.upc > 1) ? al16(4 * (size_t)p.g.unit_max + 64) : al16(p.g.unit_max) + (codec == ANSW ? 448 : 192);
+    if (codec == ANSW && (chunk_len & 3)) return TRC_E_ARG;                                   // our own format: calls start 4-byte aligned
     p.rec_stride = blocked ? (((size_t)2 * p.g.unit_max + 3) & ~(size_t)3) + 16 : 0;
     p.o1_threads = 0;
     // (order-1 tables live in shared memory since the warp-cooperative kernels; no global table scratch)
@@ -152,8 +154,9 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
     g_prof_n = 0;
     const bool v2 = codec_static(codec) && v2_ok(d_in, chunk_len, chunks_per_cdf);
+    if (codec == ANSW && !(((uintptr_t)d_in & 3) == 0 && (chunks_per_cdf == 0 || chunks_per_cdf % V2_NT == 0))) return TRC_E_ARG;
     TableSet *tabs = (TableSet *)(sc + p.off_tabs);
-    if (v2) {   // symbol tables once per launch
+    if (v2 || codec == ANSW) {   // symbol tables once per launch
         k_build_tables<<<dim3((unsigned)n_tables(g.n_calls, chunks_per_cdf), 1), 256, 0, st>>>(d_cdf, cdfnum, tabs, 0);
         CK_LAUNCH();
     }
@@ -165,6 +168,7 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
                 else k_rc_static_enc<1><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
     case RCS2:  if (v2) k_rcs2_enc_lpc<<<blocks(g.n_calls, LPC_NT / 2), LPC_NT, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
                 else k_rc_static_enc<2><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
+    case ANSW:  k_answ_enc<<<blocks(g.n_calls, ANSW_WPB), ANSW_WPB * 32, 0, st>>>(d_in, g, tabs, chunks_per_cdf, slots, p.slot_stride, meta); break;
     case ANS4:  k_rans_adapt_enc<M_NIB, AD_NT_NIB><<<blocks(g.n_units, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta); break;
     // adaptive byte rANS: many small units -> one lane per unit (throughput); few large units -> one warp per unit (latency)
     case ANS:   if (g.n_units >= COOP_MIN_LANE_UNITS) k_rans_adapt_enc<M_BYTE, AD_NT_BYTE><<<blocks(g.n_units, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta);
@@ -208,7 +212,8 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
     Geom g = p.g; g.upc = 1; g.n_units = g.n_calls;     // decoders work per call
     auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
     g_prof_n = 0;
-    if (codec_static(codec) && v2_ok(d_out, chunk_len, chunks_per_cdf) && ((uintptr_t)d_in & 15) == 0) {
+    if (codec == ANSW && !((((uintptr_t)d_in | (uintptr_t)d_out) & 3) == 0 && (chunks_per_cdf == 0 || chunks_per_cdf % V2_NT == 0))) return TRC_E_ARG;
+    if (codec == ANSW || (codec_static(codec) && v2_ok(d_out, chunk_len, chunks_per_cdf) && ((uintptr_t)d_in & 15) == 0)) {
         // decode-side tables come from the stream-ordered allocator; keep its pool from trimming back to the OS
         // at every synchronisation (the default release threshold of 0 makes each call pay a fresh cuMemMap)
         static int s_pool_dev = -1;
@@ -224,7 +229,8 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
         k_build_tables<<<dim3((unsigned)nt, 1 + LUT_PARTS), 1024, 0, st>>>(d_cdf, cdfnum, tabs, 1);
         g_launches++;
         prof_mark(st);
-        if (codec == ANS4S) k_rans_static_dec_v2<<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, chunks_per_cdf, flags);
+        if (codec == ANSW) k_answ_dec<<<blocks(g.n_calls, ANSW_WPB), ANSW_WPB * 32, 0, st>>>(d_in, d_in_off, d_out, g, tabs, chunks_per_cdf);
+        else if (codec == ANS4S) k_rans_static_dec_v2<<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, chunks_per_cdf, flags);
         else if (codec == RCS) k_rc_static_dec_v2<1><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf);
         else k_rcs2_dec_lpc<<<blocks(g.n_calls, LPC_NT / 2), LPC_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf);
         g_launches++; prof_mark(st);
