@@ -123,6 +123,7 @@ def run_reference(args):
     for _ in range(max(args.warmup, 1)):
         r = cpu_reference_run(codec, data, cdf, threads, 1, sample_bytes)
     es = ds = 0.0
+    args.steps = min(args.steps, 20)             # each step is ~0.2-0.5 s of CPU work on the bounded sample; keep the arm to minutes
     for _ in range(args.steps):
         r = cpu_reference_run(codec, data, cdf, threads, 1, sample_bytes)
         assert r["ok"], "reference round trip failed"
@@ -360,8 +361,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--codec", default="rcs2", choices=sorted(CODECS))
     ap.add_argument("--chunk", type=int, default=4096)

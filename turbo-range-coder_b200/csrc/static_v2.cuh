@@ -432,8 +432,10 @@ struct RcDRing {
     uint32_t bad;
     __device__ __forceinline__ void step(const uint8_t *lut, const uint32_t *dtab, const uint32_t *ring, uint32_t &x_out) {
         rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;                    // _rccdfrange
-        const float qf = __ull2float_rz((uint64_t)ch << 32 | cl) * rcp_approx(__ull2float_rn((uint64_t)rh << 32 | rl));
-        const uint32_t q = __float_as_uint((fminf(qf, 32767.0f) - 0.5f) + 12582912.0f) & 0xffffu;
+        // floor(code/range) without a float->int conversion: (q - 0.5) + 1.5*2^23 rounds to nearest and leaves the integer
+        // in the low mantissa bits; the mask keeps garbage streams inside the LUT
+        const float qf = fmaf(__ull2float_rz((uint64_t)ch << 32 | cl), rcp_approx(__ull2float_rn((uint64_t)rh << 32 | rl)), -0.5f);
+        const uint32_t q = __float_as_uint(qf + 12582912.0f) & 0x7fffu;
         const uint32_t x = lut[q], e = dtab[x];
         const uint32_t c0 = e >> 16, f = e & 0xffffu;
         const uint32_t pl = rl * c0, ph = __umulhi(rl, c0) + rh * c0;                 // rp = cdf[x] * range
