@@ -41,6 +41,7 @@ REF_FN = {0: ("anscdf4senc", "anscdf4sdec"), 1: ("anscdf4enc", "anscdf4dec"), 2:
           9: ("rccdf4ienc", "rccdf4idec"),
           10: ("answenc", "answdec")}       # this repository's 32-way interleaved static rANS: no reference function, CPU leg = oracle port
 METRIC = "encode+decode GB/s on 100MB order-0 byte stream; bitstream bit-exact vs ref"
+SRC_NAME = {"zipf": "Zipf(1.1)", "bwt": "BWT-shaped", "o1": "order-1 Markov", "uniform": "uniform random"}
 
 
 def peaks():
@@ -93,8 +94,14 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted({norm.get(r, r) for r in self.reasons} - {"gpu_idle"})}
 
 
-def make_data(size, rank=0):
+def make_data(size, rank=0, src="zipf"):
     dg = importlib.import_module("turbo-range-coder_b200.datagen")
+    if src == "bwt":
+        return dg.bwt_shaped(size, seed=dg.BWT_SEED + rank)
+    if src == "o1":
+        return dg.markov1(size, seed=dg.O1_SEED + rank)
+    if src == "uniform":
+        return dg.uniform(size, seed=1 + rank)
     return dg.zipf(size, seed=dg.ZIPF_SEED + rank)
 
 
@@ -117,7 +124,7 @@ def run_reference(args):
     codec = CODECS[args.codec]
     threads = os.cpu_count() or 1
     sample_bytes = min(args.size, (8 << 20) * threads)
-    data = make_data(sample_bytes)
+    data = make_data(sample_bytes, 0, args.src)
     lib = cpu.ref() or cpu.port()
     cdf = lib.cdfini(data)
     for _ in range(max(args.warmup, 1)):
@@ -135,7 +142,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round((es + ds) * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{args.size} B Zipf(1.1) bytes, static CDF, codec {args.codec}", "codec": args.codec},
+            "config": {"workload": f"{args.size} B {SRC_NAME[args.src]} bytes, codec {args.codec}", "codec": args.codec},
             "enc_gbs": round(sample_bytes / es / 1e9, 4), "dec_gbs": round(sample_bytes / ds / 1e9, 4),
             "ratio": round(r["clen"] / sample_bytes, 5),
             "cpu_baseline": {"value": round(val, 4), "unit": "GB/s", "cores": threads, "kind": r["kind"], "sample": sample},
@@ -163,15 +170,18 @@ def run_ours(args):
     size, chunk = args.size, args.chunk
     static = codec in (0, 4, 5, 10)
 
-    data = make_data(size, rank)
+    data = make_data(size, rank, args.src)
     if codec in (0, 1, 8, 9) and not (codec == 0 and args.bytes_alphabet):   # 16-symbol codecs get the low nibbles
         data = data & 15
     d_in = torch.from_numpy(data).to(dev)
     batch = trc.DeviceBatch(codec, size, chunk, cdfnum=(256 if static else 0), device=dev)
     if static:                                    # cdfini on the device, outside the timed region (turborc.c:429-433)
-        cdf_dev, status = trc.cdfini_dev(d_in, size, size)
+        blk = args.cdf_block if args.cdf_block else size      # one table per cdf-block bytes (BASELINE config 5: 64 MB blocks)
+        assert blk % chunk == 0, "--cdf-block must be a multiple of --chunk"
+        cdf_dev, status = trc.cdfini_dev(d_in, size, blk)
         assert int(status.abs().sum().item()) == 0
         batch.cdf = cdf_dev
+        batch.cpc = blk // chunk if args.cdf_block else 0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     # ---- correctness gate (untimed): round trip on the device, packed stream vs the oracle on a bounded prefix ----
@@ -293,9 +303,9 @@ def run_ours(args):
     te = td = 0.0
     for k in range(2 + e2e_steps):
         a = time.perf_counter()
-        s_out, s_off = trc.enc_batch_host(codec, h_in, chunk, cdf=cdf_h, cdfnum=256 if static else 0, out=h_out, off=h_off)
+        s_out, s_off = trc.enc_batch_host(codec, h_in, chunk, cdf=cdf_h, cdfnum=256 if static else 0, chunks_per_cdf=batch.cpc, out=h_out, off=h_off)
         b = time.perf_counter()
-        trc.dec_batch_host(codec, s_out, s_off, size, chunk, cdf=cdf_h, cdfnum=256 if static else 0, out=h_back)
+        trc.dec_batch_host(codec, s_out, s_off, size, chunk, cdf=cdf_h, cdfnum=256 if static else 0, chunks_per_cdf=batch.cpc, out=h_back)
         c = time.perf_counter()
         if k >= 2:
             te += b - a; td += c - b
@@ -333,7 +343,7 @@ def run_ours(args):
         threads = os.cpu_count() or 1
         sample_bytes = min(size, (8 << 20) * threads)
         from oracle import cpu
-        cdfh = (cpu.ref() or cpu.port()).cdfini(data[:sample_bytes]) if static else None
+        cdfh = (cpu.ref() or cpu.port()).cdfini(data[:sample_bytes]) if static else None     # (one table for the CPU sample)
         r = cpu_reference_run(codec, data, cdfh, threads, 2, sample_bytes)
         one = cpu_reference_run(codec, data, cdfh, 1, 1, min(sample_bytes, 16 << 20))
         cpu_baseline = {"value": round(sample_bytes / (r["enc_s"] + r["dec_s"]) / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": r["kind"],
@@ -344,8 +354,8 @@ def run_ours(args):
     line = {"metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": f"{size} B Zipf(1.1) bytes per GPU, static CDF (cdfini on the whole buffer), batch of {chunk}-byte chunks, "
-                                   f"each chunk == one reference call ({REF_FN[codec][0]}/{REF_FN[codec][1]})",
+            "config": {"workload": f"{size} B {SRC_NAME[args.src]} bytes per GPU, " + (("static CDF (cdfini per " + (str(args.cdf_block) + "-byte block" if args.cdf_block else "whole buffer") + "), ") if static else "adaptive model, ") +
+                                   f"batch of {chunk}-byte chunks, each chunk == one reference call ({REF_FN[codec][0]}/{REF_FN[codec][1]})",
                        "codec": args.codec, "chunk_bytes": chunk, "n_chunks": n_chunks, "l2": "flushed (256 MiB write) before each timed encode and decode",
                        "multi_gpu": f"independent shard per rank, packed streams gathered on rank 0 inside the step: {gather_kind}" if world > 1 else "single GPU"},
             "enc_gbs": round(total_bytes / (enc_ms * 1e-3) / 1e9, 3), "dec_gbs": round(total_bytes / (dec_ms * 1e-3) / 1e9, 3),
@@ -368,6 +378,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=4096)
     ap.add_argument("--size", type=int, default=100_000_000)
     ap.add_argument("--bytes-alphabet", action="store_true", help="ans4s: code full bytes with a 256-entry table")
+    ap.add_argument("--src", default="zipf", choices=["zipf", "bwt", "o1", "uniform"], help="synthetic source (SURVEY.md section 8d)")
+    ap.add_argument("--cdf-block", type=int, default=0, help="static codecs: one cdfini table per this many bytes (0 = whole buffer)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_ours(args)

@@ -359,7 +359,8 @@ Ctx g_ctx;
 
 // Sub-batching for the host-pointer calls: upload of sub-batch i+1, coding of i and download of i-1 overlap on
 // three streams, so a host->host call costs about max(H2D, D2H) instead of their sum.  Sub-batches are whole
-// calls, aligned to table groups, ~8 MiB each, at most 64.
+// calls, aligned to table groups, ~8 MiB each, at most 64, and only when a sub-batch still holds >= 1024 calls (the
+// coders are latency-bound per call: a launch with few calls takes as long as one with thousands).
 constexpr size_t SUB_BYTES = 8u << 20;
 static size_t sub_calls(size_t n_calls, size_t chunk_len, size_t cpc) {
     size_t gsz = SUB_BYTES / chunk_len;
@@ -465,7 +466,7 @@ int host_enc(int codec, const unsigned char *in, size_t total_len, size_t chunk_
     const size_t n = p.g.n_calls;
     if (p.g.upc == 1 && total_len >= 4 * SUB_BYTES && chunk_len <= SUB_BYTES) {
         const size_t gsz = sub_calls(n, chunk_len, chunks_per_cdf);
-        if (gsz < n) return host_enc_pipelined(c, codec, in, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, out, out_off, out_len, n, gsz);
+        if (gsz < n && gsz >= 1024) return host_enc_pipelined(c, codec, in, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, out, out_off, out_len, n, gsz);
     }
     if ((rc = c.in.need(total_len + 64)) || (rc = c.out.need(trc_enc_bound(total_len, chunk_len))) ||
         (rc = c.off.need((n + 1) * 8)) || (rc = c.scratch.need(p.total + 256))) return rc;
@@ -506,7 +507,7 @@ int host_dec(int codec, const unsigned char *in, const uint64_t *in_off, size_t 
     const size_t n = p.g.n_calls;
     if (total_len >= 4 * SUB_BYTES && chunk_len <= SUB_BYTES && in_bytes == (size_t)in_off[n]) {
         const size_t gsz = sub_calls(n, chunk_len, chunks_per_cdf);
-        if (gsz < n) return host_dec_pipelined(c, codec, in, in_off, out, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, flags, n, gsz);
+        if (gsz < n && gsz >= 1024) return host_dec_pipelined(c, codec, in, in_off, out, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, flags, n, gsz);
     }
     if ((rc = c.in.need(in_bytes + 64)) || (rc = c.out.need(total_len + 64)) || (rc = c.off.need((n + 1) * 8))) return rc;
     CK(cudaMemcpyAsync(c.off.p, in_off, (n + 1) * 8, cudaMemcpyHostToDevice, c.st));
