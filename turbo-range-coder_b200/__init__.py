@@ -43,8 +43,11 @@ def build():
 
 
 if not os.path.exists(LIB_PATH):
-    raise ImportError(f"{LIB_PATH} is missing: build it with `make -C {_HERE}/csrc` "
-                      "(or __graft_entry__.build()).  There is no CPU fallback.")
+    try:                                       # a fresh checkout: compile once (needs nvcc; no GPU required)
+        build()
+    except Exception as e:                     # noqa: BLE001
+        raise ImportError(f"{LIB_PATH} is missing and could not be built ({e}): run `make -C {_HERE}/csrc` "
+                          "(or __graft_entry__.build()).  There is no CPU fallback.") from e
 lib = ctypes.CDLL(LIB_PATH)
 
 _sz, _vp, _u, _i = ctypes.c_size_t, ctypes.c_void_p, ctypes.c_uint, ctypes.c_int

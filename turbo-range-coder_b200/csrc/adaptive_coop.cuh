@@ -131,9 +131,9 @@ k_ans_byte_enc_coop(const uint8_t *__restrict__ in, Geom g, uint8_t *__restrict_
 // ---- decoder --------------------------------------------------------------------------------------------------
 // one-table register cache: the entry a lane owns stays in `m` while consecutive symbols select the same table
 struct TabCache {
-    uint16_t *tab; int m;
-    __device__ __forceinline__ void select(uint16_t *t, unsigned i) { if (t != tab) { tab[i] = (uint16_t)m; m = t[i]; tab = t; } }   // warp-uniform
-    __device__ __forceinline__ void flush(unsigned i) { tab[i] = (uint16_t)m; }
+    uint32_t id; int m;                                                        // id = entry offset of the cached table inside T
+    __device__ __forceinline__ void select(uint16_t *T, uint32_t t, unsigned i) { if (t != id) { T[id + i] = (uint16_t)m; m = T[t + i]; id = t; } }   // warp-uniform
+    __device__ __forceinline__ void flush(uint16_t *T, unsigned i) { T[id + i] = (uint16_t)m; }
 };
 // one nibble: cdf16ansdec (cdf_.h:52-59) + STATEUPD (cdf_.h:37); every lane returns the same x and updated state
 __device__ __forceinline__ uint32_t coop_dec_nib(TabCache &c, unsigned i, unsigned lane, uint32_t &s) {
@@ -198,22 +198,22 @@ k_ans_byte_dec_coop(const uint8_t *__restrict__ in, const uint64_t *__restrict__
             __syncwarp();
             uint32_t s0 = ws.take32(), s1 = ws.take32(), s2 = ws.take32(), s3 = ws.take32();   // mnfill anscdf_.h:176
             TabCache ch, cl;                                                   // high-nibble-type / low-nibble-type table caches
-            ch.tab = T; ch.m = T[i]; cl.tab = T + 16; cl.m = T[16 + i];
+            ch.id = 0; ch.m = T[i]; cl.id = 16; cl.m = T[16 + i];
             for (uint32_t pi = 0; pi < npairs; pi++) {                         // mndec8x2 / mndec8x2x anscdf_.h:152-174
-                uint16_t *c0 = T + (O1 ? (size_t)cx * O1_CTX_ENTRIES : 0);
-                ch.select(c0, i);
+                const uint32_t c0 = O1 ? cx * O1_CTX_ENTRIES : 0;
+                ch.select(T, c0, i);
                 const uint32_t yh0 = coop_dec_nib(ch, i, lane, s0);
-                cl.select(c0 + (1 + yh0) * 16, i);
+                cl.select(T, c0 + (1 + yh0) * 16, i);
                 const uint32_t yl0 = coop_dec_nib(cl, i, lane, s1);
                 const uint32_t x0 = yh0 << 4 | yl0;
-                uint16_t *c1 = T + (O1 ? (size_t)x0 * O1_CTX_ENTRIES : 0);
-                ch.select(c1, i);
+                const uint32_t c1 = O1 ? x0 * O1_CTX_ENTRIES : 0;
+                ch.select(T, c1, i);
                 const uint32_t yh1 = coop_dec_nib(ch, i, lane, s2);
-                cl.select(c1 + (1 + yh1) * 16, i);
+                cl.select(T, c1 + (1 + yh1) * 16, i);
                 const uint32_t yl1 = coop_dec_nib(cl, i, lane, s3);
                 const uint32_t x1 = yh1 << 4 | yl1;
                 cx = x1;
-                // ecdnorm x4 in state order (anscdf_.h:158-161)
+                // ecdnorm x4 in state order (anscdf_.h:158-161); the states are replicated, so these branches are warp-uniform
                 if (s0 < ANS_L) s0 = s0 << 16 | ws.take16();
                 if (s1 < ANS_L) s1 = s1 << 16 | ws.take16();
                 if (s2 < ANS_L) s2 = s2 << 16 | ws.take16();
@@ -227,7 +227,7 @@ k_ans_byte_dec_coop(const uint8_t *__restrict__ in, const uint64_t *__restrict__
                     } else bo[o] = (uint8_t)x0;                                // odd tail: second byte discarded (anscdf.c:602)
                 }
             }
-            ch.flush(i); cl.flush(i);                                          // (tables are re-initialised for the next block anyway)
+            ch.flush(T, i); cl.flush(T, i);                                    // (tables are re-initialised for the next block anyway)
         }
     }
 }
@@ -398,10 +398,10 @@ k_rc_byte_dec_coop(const uint8_t *__restrict__ in, const uint64_t *__restrict__ 
             w0.init(stream + 4, gend); d0.init(w0); w1.init(p1, gend); d1.init(w1);
         }
         TabCache ch, cl;
-        ch.tab = T; ch.m = T[i]; cl.tab = T + 16; cl.m = T[16 + i];
+        ch.id = 0; ch.m = T[i]; cl.id = 16; cl.m = T[16 + i];
         for (size_t k = 0; k < n; k++) {                                         // cdf8d / cdf8d2 rccdf_.h:50-73
             const uint32_t yh = d0.nib(ch, i, lane, w0);
-            cl.select(T + (1 + yh) * 16, i);
+            cl.select(T, (1 + yh) * 16, i);
             const uint32_t yl = NC == 1 ? d0.nib(cl, i, lane, w0) : d1.nib(cl, i, lane, w1);
             if (lane == 0) op[k] = (uint8_t)(yh << 4 | yl);
         }
