@@ -332,7 +332,7 @@ def run_ours(args):
     achieved = alg / (kern_ms[dom] * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and size == 100_000_000 and chunk == 4096 and args.src == "zipf":   # the capture is of this exact workload
         traffic = json.load(open(tp)).get(f"{args.codec}/{dom}")
     roofline = {"bound": "hbm", "kernel": f"{args.codec}/{dom}", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
