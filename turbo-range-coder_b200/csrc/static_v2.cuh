@@ -80,7 +80,8 @@ __device__ __forceinline__ void tma_wait(uint64_t *bar) {
 __device__ __forceinline__ uint4 ldg128(const uint8_t *p) { return __ldg((const uint4 *)p); }
 
 constexpr int V2_NT = 128;
-constexpr int LPC_NT = 128;                       // lane-per-coder kernels: 64 calls per CTA
+constexpr int LPC_NT = 128;                       // lane-per-coder kernels: 64 calls per CTA by default
+constexpr int LPC_MAX_NT = 512;                   // ... up to 256 calls per CTA when the batch is sized to one CTA per SM
 
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
@@ -430,7 +431,7 @@ struct RcDRing {
     uint32_t n0, n1;                // next two stream words (already in registers)
     uint32_t ci;                    // ring read cursor: absolute word index (relative to qbase) of the next word to move into n1
     uint32_t bad;
-    __device__ __forceinline__ void step(const uint8_t *lut, const uint32_t *dtab, const uint32_t *ring, uint32_t &x_out) {
+    __device__ __forceinline__ void step(const uint8_t *lut, const uint32_t *dtab, const uint32_t *ring, uint32_t rstride, uint32_t &x_out) {
         rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;                    // _rccdfrange
         // floor(code/range) without a float->int conversion: (q - 0.5) + 1.5*2^23 rounds to nearest and leaves the integer
         // in the low mantissa bits; the mask keeps garbage streams inside the LUT
@@ -447,7 +448,7 @@ struct RcDRing {
         rh = p ? fl : fh; rl = p ? 0u : fl;
         ch = p ? dl : dh; cl = p ? n0 : dl;
         n0 = p ? n1 : n0;
-        if (p) n1 = ring[(ci & (RING_W - 1)) * LPC_NT];
+        if (p) n1 = ring[(ci & (RING_W - 1)) * rstride];
         ci += p ? 1u : 0u;
         x_out = x;
     }
@@ -478,18 +479,21 @@ struct RcDExact {
 // at the end.
 // =========================================================================================================
 
-__global__ void __launch_bounds__(LPC_NT)
+// calls_per_cta: LPC_NT/2 for big batches; for batches of about one wave the host sizes the CTAs so that every SM gets
+// the same number of coders (ceil(n_calls / #SM) calls per CTA, one CTA per SM): with 2-3 CTAs per SM the fuller SMs
+// would set the kernel time.
+__global__ void __launch_bounds__(LPC_MAX_NT, 1)
 k_rcs2_enc_lpc(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const TableSet *__restrict__ ts, size_t cpc,
-               uint8_t *__restrict__ slots, size_t slot_stride, UnitMeta *__restrict__ meta) {
+               uint8_t *__restrict__ slots, size_t slot_stride, UnitMeta *__restrict__ meta, unsigned calls_per_cta) {
     __shared__ __align__(16) uint32_t ctab[256];
     __shared__ uint64_t bar;
-    const size_t j0 = (size_t)blockIdx.x * (LPC_NT / 2), j = j0 + (threadIdx.x >> 1);
+    const size_t j0 = (size_t)blockIdx.x * calls_per_cta, j = j0 + (threadIdx.x >> 1);
     const unsigned c = threadIdx.x & 1;
     const TableSet *t = ts + (cpc ? j0 / cpc : 0);
     if (threadIdx.x == 0) tma_fetch(ctab, t->ctab, sizeof ctab, &bar);
     __syncthreads();
     tma_wait(&bar);
-    const bool live = j < n_calls;                 // dead lanes still take part in the shuffles below
+    const bool live = j < n_calls && (threadIdx.x >> 1) < calls_per_cta;   // dead lanes still take part in the shuffles below
     size_t start = 0, n = 0;
     if (live) call_span(g, j, start, n);
     const uint8_t *ip = in + start;
@@ -542,14 +546,15 @@ k_rcs2_enc_lpc(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const Tab
     meta[j] = m;
 }
 
-__global__ void __launch_bounds__(LPC_NT)
+__global__ void __launch_bounds__(LPC_MAX_NT, 1)
 k_rcs2_dec_lpc(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint8_t *__restrict__ out, Geom g,
-               size_t n_calls, const TableSet *__restrict__ ts, unsigned cdfnum, size_t cpc) {
+               size_t n_calls, const TableSet *__restrict__ ts, unsigned cdfnum, size_t cpc, unsigned calls_per_cta) {
     __shared__ __align__(16) uint32_t dtab[256];
     __shared__ __align__(16) uint8_t lut[PROB_TOTAL];
-    __shared__ uint32_t ringbuf[RING_W * LPC_NT];
+    extern __shared__ uint32_t ringbuf[];                                             // RING_W * blockDim.x words
     __shared__ uint64_t bar;
-    const size_t j0 = (size_t)blockIdx.x * (LPC_NT / 2), j = j0 + (threadIdx.x >> 1);
+    const uint32_t rstride = blockDim.x;
+    const size_t j0 = (size_t)blockIdx.x * calls_per_cta, j = j0 + (threadIdx.x >> 1);
     const unsigned c = threadIdx.x & 1;
     const TableSet *t = ts + (cpc ? j0 / cpc : 0);
     if (threadIdx.x == 0) {
@@ -564,7 +569,7 @@ k_rcs2_dec_lpc(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
     }
     __syncthreads();
     tma_wait(&bar);
-    const bool live = j < n_calls;
+    const bool live = j < n_calls && (threadIdx.x >> 1) < calls_per_cta;
     size_t start = 0, n = 0;
     uint64_t so = 0, sl = 0;
     if (live) { call_span(g, j, start, n); so = in_off[j]; sl = in_off[j + 1] - so; }
@@ -590,8 +595,8 @@ k_rcs2_dec_lpc(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
     };
     uint32_t *ring = ringbuf + threadIdx.x;
     auto ring_put = [&](uint32_t w, const uint4 &v) {                                 // w multiple of 4
-        ring[((w + 0) & (RING_W - 1)) * LPC_NT] = v.x; ring[((w + 1) & (RING_W - 1)) * LPC_NT] = v.y;
-        ring[((w + 2) & (RING_W - 1)) * LPC_NT] = v.z; ring[((w + 3) & (RING_W - 1)) * LPC_NT] = v.w;
+        ring[((w + 0) & (RING_W - 1)) * rstride] = v.x; ring[((w + 1) & (RING_W - 1)) * rstride] = v.y;
+        ring[((w + 2) & (RING_W - 1)) * rstride] = v.z; ring[((w + 3) & (RING_W - 1)) * rstride] = v.w;
     };
     RcDRing d;
     uint32_t fi;                                                                      // words [fi-RING_W, fi) are in the ring
@@ -599,7 +604,7 @@ k_rcs2_dec_lpc(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
         fi = w0 & ~3u;
         for (int k = 0; k < 3; k++) { ring_put(fi, gquad(fi)); fi += 4; }
         d.rl = (uint32_t)range; d.rh = (uint32_t)(range >> 32); d.cl = (uint32_t)code; d.ch = (uint32_t)(code >> 32);
-        d.n0 = ring[(w0 & (RING_W - 1)) * LPC_NT]; d.n1 = ring[((w0 + 1) & (RING_W - 1)) * LPC_NT];
+        d.n0 = ring[(w0 & (RING_W - 1)) * rstride]; d.n1 = ring[((w0 + 1) & (RING_W - 1)) * rstride];
         d.ci = w0 + 2; d.bad = 0;
     };
     {
@@ -617,9 +622,9 @@ k_rcs2_dec_lpc(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_o
             const RcDRing s0 = d;                                                     // block start state (for the redo path)
             uint32_t x;
 #pragma unroll
-            for (int k = 0; k < 4; k++) { d.step(lut, dtab, ring, x); a0 |= x << (8 * k); }
+            for (int k = 0; k < 4; k++) { d.step(lut, dtab, ring, rstride, x); a0 |= x << (8 * k); }
 #pragma unroll
-            for (int k = 0; k < 4; k++) { d.step(lut, dtab, ring, x); a1 |= x << (8 * k); }
+            for (int k = 0; k < 4; k++) { d.step(lut, dtab, ring, rstride, x); a1 |= x << (8 * k); }
             const bool dry = d.ci > fi;                                               // a read ran past the filled part of the ring
             if (need) { ring_put(fi, t4); fi += 4; }
             if (__builtin_expect(d.bad != 0 || dry, 0)) {                             // estimate missed (or ring ran dry): exact redo

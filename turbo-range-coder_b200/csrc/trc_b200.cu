@@ -50,6 +50,15 @@ struct Plan {
 // tables needed for n calls when `cpc` consecutive calls share one (0 = one table for everything)
 static inline size_t n_tables(size_t n_calls, size_t cpc) { return cpc ? (n_calls + cpc - 1) / cpc : 1; }
 // the throughput kernels (static_v2.cuh) need 16-byte aligned calls and table groups that do not split a CTA
+// lane-per-coder launch shape: (calls per CTA, CTAs).  Batches that fit one wave get one equally loaded CTA per SM.
+static void lpc_shape(size_t n_calls, size_t cpc, unsigned &calls_per_cta, unsigned &ctas) {
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+    calls_per_cta = LPC_NT / 2;
+    const size_t per_sm = (n_calls + n_sm - 1) / n_sm;
+    if (cpc == 0 && per_sm > LPC_NT / 2 && per_sm <= LPC_MAX_NT / 2) calls_per_cta = (unsigned)per_sm;
+    ctas = (unsigned)((n_calls + calls_per_cta - 1) / calls_per_cta);
+}
 static inline bool v2_ok(const void *buf, size_t chunk_len, size_t cpc) {
     return ((uintptr_t)buf & 15) == 0 && (chunk_len & 15) == 0 && (cpc == 0 || cpc % V2_NT == 0);
 }
@@ -166,7 +175,8 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
                 else k_rans_static_enc<<<blocks(g.n_calls, RANS_S_NT), RANS_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
     case RCS:   if (v2) k_rc_static_enc_v2<1><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
                 else k_rc_static_enc<1><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
-    case RCS2:  if (v2) k_rcs2_enc_lpc<<<blocks(g.n_calls, LPC_NT / 2), LPC_NT, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
+    case RCS2:  if (v2) { unsigned cpcta, ctas; lpc_shape(g.n_calls, chunks_per_cdf, cpcta, ctas);
+                          k_rcs2_enc_lpc<<<ctas, (2 * cpcta + 31) & ~31u, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta, cpcta); }
                 else k_rc_static_enc<2><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
     case ANSW:  k_answ_enc<<<blocks(g.n_calls, ANSW_WPB), ANSW_WPB * 32, 0, st>>>(d_in, g, tabs, chunks_per_cdf, slots, p.slot_stride, meta); break;
     case ANS4:  k_rans_adapt_enc<M_NIB, AD_NT_NIB><<<blocks(g.n_units, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta); break;
@@ -232,7 +242,11 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
         if (codec == ANSW) k_answ_dec<<<blocks(g.n_calls, ANSW_WPB), ANSW_WPB * 32, 0, st>>>(d_in, d_in_off, d_out, g, tabs, chunks_per_cdf);
         else if (codec == ANS4S) k_rans_static_dec_v2<<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, chunks_per_cdf, flags);
         else if (codec == RCS) k_rc_static_dec_v2<1><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf);
-        else k_rcs2_dec_lpc<<<blocks(g.n_calls, LPC_NT / 2), LPC_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf);
+        else { unsigned cpcta, ctas; lpc_shape(g.n_calls, chunks_per_cdf, cpcta, ctas);
+               const unsigned nt = (2 * cpcta + 31) & ~31u;
+               static bool attr = false;
+               if (!attr) { CK(cudaFuncSetAttribute(k_rcs2_dec_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RING_W * LPC_MAX_NT * sizeof(uint32_t)))); attr = true; }
+               k_rcs2_dec_lpc<<<ctas, nt, RING_W * nt * sizeof(uint32_t), st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf, cpcta); }
         g_launches++; prof_mark(st);
         cudaError_t e = cudaPeekAtLastError();
         cudaFreeAsync(tabs, st);
