@@ -177,7 +177,7 @@ def run_ours(args):
     batch = trc.DeviceBatch(codec, size, chunk, cdfnum=(256 if static else 0), device=dev)
     if static:                                    # cdfini on the device, outside the timed region (turborc.c:429-433)
         blk = args.cdf_block if args.cdf_block else size      # one table per cdf-block bytes (BASELINE config 5: 64 MB blocks)
-        assert blk % chunk == 0, "--cdf-block must be a multiple of --chunk"
+        assert not args.cdf_block or blk % chunk == 0, "--cdf-block must be a multiple of --chunk"
         cdf_dev, status = trc.cdfini_dev(d_in, size, blk)
         assert int(status.abs().sum().item()) == 0
         batch.cdf = cdf_dev
