@@ -133,12 +133,12 @@ struct RcEncV2 {
 // testing once per 16-byte block and once after the last symbol decides the same way.
 // =========================================================================================================
 template <int NC>
-__global__ void __launch_bounds__(V2_NT)
+__global__ void __launch_bounds__(LPC_MAX_NT, 1)
 k_rc_static_enc_v2(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const TableSet *__restrict__ ts, size_t cpc,
                    uint8_t *__restrict__ slots, size_t slot_stride, UnitMeta *__restrict__ meta) {
     __shared__ __align__(16) uint32_t ctab[256];
     __shared__ uint64_t bar;
-    const size_t j0 = (size_t)blockIdx.x * V2_NT, j = j0 + threadIdx.x;
+    const size_t j0 = (size_t)blockIdx.x * blockDim.x, j = j0 + threadIdx.x;   // CTA size is chosen by the host (v2_shape)
     const TableSet *t = ts + (cpc ? j0 / cpc : 0);
     if (threadIdx.x == 0) tma_fetch(ctab, t->ctab, sizeof ctab, &bar);
     __syncthreads();
@@ -241,13 +241,13 @@ struct RcDec2 {
 };
 
 template <int NC>
-__global__ void __launch_bounds__(V2_NT)
+__global__ void __launch_bounds__(LPC_MAX_NT, 1)
 k_rc_static_dec_v2(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint8_t *__restrict__ out, Geom g,
                    size_t n_calls, const TableSet *__restrict__ ts, unsigned cdfnum, size_t cpc) {
     __shared__ __align__(16) uint32_t dtab[256];
     __shared__ __align__(16) uint8_t lut[PROB_TOTAL];
     __shared__ uint64_t bar;
-    const size_t j0 = (size_t)blockIdx.x * V2_NT, j = j0 + threadIdx.x;
+    const size_t j0 = (size_t)blockIdx.x * blockDim.x, j = j0 + threadIdx.x;   // CTA size is chosen by the host (v2_shape)
     const TableSet *t = ts + (cpc ? j0 / cpc : 0);
     if (threadIdx.x == 0) {
         uint32_t b = smem_u32(&bar);
@@ -671,12 +671,12 @@ __device__ __forceinline__ uint32_t rans_enc_step_v2(uint32_t s, const uint4 e, 
     return s + e.w + q * (e.z & 0xffffu);
 }
 
-__global__ void __launch_bounds__(V2_NT)
+__global__ void __launch_bounds__(LPC_MAX_NT, 1)
 k_rans_static_enc_v2(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const TableSet *__restrict__ ts, size_t cpc,
                      uint8_t *__restrict__ slots, size_t slot_stride, UnitMeta *__restrict__ meta) {
     __shared__ __align__(16) uint4 etab[256];
     __shared__ uint64_t bar;
-    const size_t j0 = (size_t)blockIdx.x * V2_NT, j = j0 + threadIdx.x;
+    const size_t j0 = (size_t)blockIdx.x * blockDim.x, j = j0 + threadIdx.x;   // CTA size is chosen by the host (v2_shape)
     const TableSet *t = ts + (cpc ? j0 / cpc : 0);
     if (threadIdx.x == 0) tma_fetch(etab, t->etab, sizeof etab, &bar);
     __syncthreads();
@@ -744,14 +744,15 @@ struct RansReader2 {
     }
 };
 
-__global__ void __launch_bounds__(V2_NT)
+__global__ void __launch_bounds__(LPC_MAX_NT, 1)
 k_rans_static_dec_v2(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint8_t *__restrict__ out, Geom g,
                      size_t n_calls, const TableSet *__restrict__ ts, size_t cpc, unsigned flags) {
     __shared__ __align__(16) uint32_t dtab[256];
     __shared__ __align__(16) uint8_t lut[PROB_TOTAL];
-    __shared__ uint32_t ringbuf[RING_W * V2_NT];
+    extern __shared__ uint32_t ringbuf[];                                             // RING_W * blockDim.x words
+    const uint32_t V2S = blockDim.x;
     __shared__ uint64_t bar;
-    const size_t j0 = (size_t)blockIdx.x * V2_NT, j = j0 + threadIdx.x;
+    const size_t j0 = (size_t)blockIdx.x * blockDim.x, j = j0 + threadIdx.x;   // CTA size is chosen by the host (v2_shape)
     const TableSet *t = ts + (cpc ? j0 / cpc : 0);
     if (threadIdx.x == 0) {
         uint32_t b = smem_u32(&bar);
@@ -790,10 +791,10 @@ k_rans_static_dec_v2(const uint8_t *__restrict__ in, const uint64_t *__restrict_
     };
     uint32_t *ring = ringbuf + threadIdx.x;
     auto ring_put = [&](uint32_t w, const uint4 &v) {
-        ring[((w + 0) & (RING_W - 1)) * V2_NT] = v.x; ring[((w + 1) & (RING_W - 1)) * V2_NT] = v.y;
-        ring[((w + 2) & (RING_W - 1)) * V2_NT] = v.z; ring[((w + 3) & (RING_W - 1)) * V2_NT] = v.w;
+        ring[((w + 0) & (RING_W - 1)) * V2S] = v.x; ring[((w + 1) & (RING_W - 1)) * V2S] = v.y;
+        ring[((w + 2) & (RING_W - 1)) * V2S] = v.z; ring[((w + 3) & (RING_W - 1)) * V2S] = v.w;
     };
-    auto ring_hw = [&](uint32_t h) -> uint32_t { uint32_t w = ring[((h >> 1) & (RING_W - 1)) * V2_NT]; return (h & 1) ? w >> 16 : w & 0xffffu; };
+    auto ring_hw = [&](uint32_t h) -> uint32_t { uint32_t w = ring[((h >> 1) & (RING_W - 1)) * V2S]; return (h & 1) ? w >> 16 : w & 0xffffu; };
     uint32_t hi = (uint32_t)(((uintptr_t)p & 15) >> 1);
     uint32_t fi = 0;                                                                  // words [.., fi) are in the ring
     for (int k = 0; k < 3; k++) { ring_put(fi, gquad(fi)); fi += 4; }
@@ -804,7 +805,7 @@ k_rans_static_dec_v2(const uint8_t *__restrict__ in, const uint64_t *__restrict_
         _s_ = (e_ & 0xffffu) * (_s_ >> PROB_BITS) + r_ - (e_ >> 16);                  /* STATEUPD cdf_.h:37 */ \
         const bool p_ = _s_ < ANS_L;                                                  /* ecdnorm anscdf_.h:50-73 */ \
         _s_ = p_ ? (_s_ << 16 | n0) : _s_; n0 = p_ ? n1 : n0; \
-        if (p_) { const uint32_t w_ = ring[((hi >> 1) & (RING_W - 1)) * V2_NT]; n1 = (hi & 1) ? w_ >> 16 : w_ & 0xffffu; } \
+        if (p_) { const uint32_t w_ = ring[((hi >> 1) & (RING_W - 1)) * V2S]; n1 = (hi & 1) ? w_ >> 16 : w_ & 0xffffu; } \
         hi += p_ ? 1u : 0u; _x_ = x_; }
     const uint32_t n4 = n & ~3u, n8 = n & ~7u;
     uint32_t o = 0;

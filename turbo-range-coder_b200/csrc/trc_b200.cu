@@ -59,6 +59,12 @@ static void lpc_shape(size_t n_calls, size_t cpc, unsigned &calls_per_cta, unsig
     if (cpc == 0 && per_sm > LPC_NT / 2 && per_sm <= LPC_MAX_NT / 2) calls_per_cta = (unsigned)per_sm;
     ctas = (unsigned)((n_calls + calls_per_cta - 1) / calls_per_cta);
 }
+// lane-per-call v2 kernels: threads per CTA (one call per thread), same balancing idea
+static unsigned v2_shape(size_t n_calls, size_t cpc) {
+    unsigned cpcta, ctas; lpc_shape(n_calls, cpc, cpcta, ctas);           // calls per CTA if the batch is about one wave
+    if (cpc == 0 && cpcta > (unsigned)V2_NT / 2) { unsigned nt = (cpcta + 31) & ~31u; if (nt > (unsigned)V2_NT && nt <= (unsigned)LPC_MAX_NT) return nt; }
+    return V2_NT;
+}
 static inline bool v2_ok(const void *buf, size_t chunk_len, size_t cpc) {
     return ((uintptr_t)buf & 15) == 0 && (chunk_len & 15) == 0 && (cpc == 0 || cpc % V2_NT == 0);
 }
@@ -169,11 +175,12 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
         k_build_tables<<<dim3((unsigned)n_tables(g.n_calls, chunks_per_cdf), 1), 256, 0, st>>>(d_cdf, cdfnum, tabs, 0);
         CK_LAUNCH();
     }
+    const unsigned v2nt = v2_shape(g.n_calls, chunks_per_cdf);
     prof_mark(st);
     switch (codec) {
-    case ANS4S: if (v2) k_rans_static_enc_v2<<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
+    case ANS4S: if (v2) k_rans_static_enc_v2<<<blocks(g.n_calls, v2nt), v2nt, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
                 else k_rans_static_enc<<<blocks(g.n_calls, RANS_S_NT), RANS_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
-    case RCS:   if (v2) k_rc_static_enc_v2<1><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
+    case RCS:   if (v2) k_rc_static_enc_v2<1><<<blocks(g.n_calls, v2nt), v2nt, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta);
                 else k_rc_static_enc<1><<<blocks(g.n_calls, RC_S_NT), RC_S_NT, 0, st>>>(d_in, g, d_cdf, cdfnum, chunks_per_cdf, slots, p.slot_stride, meta); break;
     case RCS2:  if (v2) { unsigned cpcta, ctas; lpc_shape(g.n_calls, chunks_per_cdf, cpcta, ctas);
                           k_rcs2_enc_lpc<<<ctas, (2 * cpcta + 31) & ~31u, 0, st>>>(d_in, g, g.n_calls, tabs, chunks_per_cdf, slots, p.slot_stride, meta, cpcta); }
@@ -240,8 +247,11 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
         g_launches++;
         prof_mark(st);
         if (codec == ANSW) k_answ_dec<<<blocks(g.n_calls, ANSW_WPB), ANSW_WPB * 32, 0, st>>>(d_in, d_in_off, d_out, g, tabs, chunks_per_cdf);
-        else if (codec == ANS4S) k_rans_static_dec_v2<<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, chunks_per_cdf, flags);
-        else if (codec == RCS) k_rc_static_dec_v2<1><<<blocks(g.n_calls, V2_NT), V2_NT, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf);
+        else if (codec == ANS4S) { const unsigned v2nt = v2_shape(g.n_calls, chunks_per_cdf);
+            static bool attr = false;
+            if (!attr) { CK(cudaFuncSetAttribute(k_rans_static_dec_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RING_W * LPC_MAX_NT * sizeof(uint32_t)))); attr = true; }
+            k_rans_static_dec_v2<<<blocks(g.n_calls, v2nt), v2nt, RING_W * v2nt * sizeof(uint32_t), st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, chunks_per_cdf, flags); }
+        else if (codec == RCS) { const unsigned v2nt = v2_shape(g.n_calls, chunks_per_cdf); k_rc_static_dec_v2<1><<<blocks(g.n_calls, v2nt), v2nt, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf); }
         else { unsigned cpcta, ctas; lpc_shape(g.n_calls, chunks_per_cdf, cpcta, ctas);
                const unsigned nt = (2 * cpcta + 31) & ~31u;
                static bool attr = false;
