@@ -7,6 +7,7 @@
 #include "adaptive.cuh"
 #include "static_v2.cuh"
 #include "adaptive_coop.cuh"
+#include "adaptive_v3.cuh"
 #include "rans_wide.cuh"
 #include "pack.cuh"
 #include <cstdio>
@@ -20,6 +21,7 @@ using namespace trc;
 static thread_local char g_err[256] = "";
 static int g_dev = 0;
 static const int g_force_redo = getenv("TRC_FORCE_REDO") ? 1 : 0;   // test hook: exercise the rare walk-back redo paths
+static const int g_adapt_v3 = getenv("TRC_ADAPT_V3") ? atoi(getenv("TRC_ADAPT_V3")) : 1;   // 0: previous generation of the adaptive byte rANS kernels (A/B runs)
 static unsigned long long g_launches = 0;       // kernels launched by this library (bench.py reports the delta)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -89,6 +91,32 @@ static int make_plan(int codec, size_t total_len, size_t chunk_len, Plan &p) {
     // room for one TableSet per V2_NT calls is the worst case the v2 path accepts (cpc >= V2_NT)
     p.off_tabs = o;  o += codec_static(codec) ? al256(((p.g.n_calls + V2_NT - 1) / V2_NT) * sizeof(TableSet)) : 0;
     p.total = o;
+    return TRC_OK;
+}
+
+static int sm_count() {
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+    return n_sm;
+}
+
+// adaptive byte rANS encoder, third generation: model pass (one warp per unit) then coding pass (one lane per state)
+static int launch_ans_enc3(bool o1, const unsigned char *d_in, const Geom &g, uint8_t *slots, size_t slot_stride, uint32_t *recs,
+                           size_t rec_stride, UnitMeta *meta, cudaStream_t st) {
+    static int s_lut_dev = -1;
+    int dev = 0; CK(cudaGetDevice(&dev));
+    if (dev != s_lut_dev) {                                     // once per process and device: attributes + reciprocal table
+        CK(cudaFuncSetAttribute(k_ans_model3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m3_warp_bytes<true>()));
+        CK(cudaFuncSetAttribute(k_ans_code3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3_LUT_BYTES));
+        k_build_rcp<<<PROB_TOTAL / 256, 256, 0, st>>>();
+        CK_LAUNCH();
+        s_lut_dev = dev;
+    }
+    if (o1) k_ans_model3<true><<<(unsigned)(g.n_units < (size_t)sm_count() ? g.n_units : (size_t)sm_count()), 32, m3_warp_bytes<true>(), st>>>(d_in, g, recs, rec_stride);
+    else    k_ans_model3<false><<<(unsigned)((g.n_units + M3_WPB - 1) / M3_WPB), M3_WPB * 32, M3_WPB * m3_warp_bytes<false>(), st>>>(d_in, g, recs, rec_stride);
+    CK_LAUNCH();
+    const size_t groups = (g.n_units + 7) / 8;
+    k_ans_code3<<<(unsigned)((groups + C3_WPB - 1) / C3_WPB), C3_WPB * 32, C3_LUT_BYTES, st>>>(g, recs, rec_stride, slots, slot_stride, meta);
     return TRC_OK;
 }
 
@@ -189,8 +217,10 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     case ANS4:  k_rans_adapt_enc<M_NIB, AD_NT_NIB><<<blocks(g.n_units, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta); break;
     // adaptive byte rANS: many small units -> one lane per unit (throughput); few large units -> one warp per unit (latency)
     case ANS:   if (g.n_units >= COOP_MIN_LANE_UNITS) k_rans_adapt_enc<M_BYTE, AD_NT_BYTE><<<blocks(g.n_units, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta);
+                else if (g_adapt_v3) { rc = launch_ans_enc3(false, d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta, st); if (rc) return rc; }
                 else k_ans_byte_enc_coop<false><<<blocks(g.n_units, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta); break;
     case ANS1: {
+        if (g_adapt_v3) { rc = launch_ans_enc3(true, d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta, st); if (rc) return rc; break; }
         static bool attr = false;
         if (!attr) { CK(cudaFuncSetAttribute(k_ans_byte_enc_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)O1_SMEM_BYTES)); attr = true; }
         k_ans_byte_enc_coop<true><<<(unsigned)(g.n_units < 148 ? g.n_units : 148), 32, O1_SMEM_BYTES, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta);
@@ -270,11 +300,14 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
     case RCS2:  k_rc_static_dec<2><<<blocks(g.n_calls, RC_SD_NT), RC_SD_NT, 0, st>>>(d_in, d_in_off, d_out, g, d_cdf, cdfnum, chunks_per_cdf); break;
     case ANS4:  k_rans_adapt_dec<M_NIB, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g, nullptr, flags); break;
     case ANS:   if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rans_adapt_dec<M_BYTE, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g, nullptr, flags);
+                else if (g_adapt_v3) k_ans_dec3<false><<<blocks(g.n_calls, 2 * D3_WPB), D3_WPB * 32, d3_smem_bytes<false>(), st>>>(d_in, d_in_off, d_out, g);
                 else k_ans_byte_dec_coop<false><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, d_in_off, d_out, g); break;
     case ANS1: {
         static bool attr = false;
-        if (!attr) { CK(cudaFuncSetAttribute(k_ans_byte_dec_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)O1_SMEM_BYTES)); attr = true; }
-        k_ans_byte_dec_coop<true><<<(unsigned)(g.n_calls < 148 ? g.n_calls : 148), 32, O1_SMEM_BYTES, st>>>(d_in, d_in_off, d_out, g);
+        if (!attr) { CK(cudaFuncSetAttribute(k_ans_byte_dec_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)O1_SMEM_BYTES));
+                     CK(cudaFuncSetAttribute(k_ans_dec3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d3_smem_bytes<true>())); attr = true; }
+        if (g_adapt_v3) k_ans_dec3<true><<<(unsigned)(g.n_calls < (size_t)sm_count() ? g.n_calls : (size_t)sm_count()), 32, d3_smem_bytes<true>(), st>>>(d_in, d_in_off, d_out, g);
+        else k_ans_byte_dec_coop<true><<<(unsigned)(g.n_calls < 148 ? g.n_calls : 148), 32, O1_SMEM_BYTES, st>>>(d_in, d_in_off, d_out, g);
         break;
     }
     case RC:    if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_dec<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g);
