@@ -8,11 +8,12 @@
 //       * cdf16upd (cdf_.h:46-50) per entry is  m' = (127 m + 10 i + (i > x ? 32736 : 0)) >> 7  -- algebraically the
 //         reference's  m += (T - m) >> 7  (floor division by 128 of a non-negative sum), i.e. ONE multiply-add and one
 //         shift on the dependent chain;
-//       * tables are write-through in shared memory; the table of byte t+1 is loaded while byte t is being updated
-//         and a select forwards the fresh entry when both bytes use the same table, so shared-memory latency is off
-//         the chain;
+//       * tables are write-through in shared memory; the table entry of byte t+2 is loaded while byte t is being
+//         updated and two selects forward the fresh entries when bytes t / t+1 hit the same table, so shared-memory
+//         latency is off the chain;
 //       * the (freq | cum << 16) record of a nibble (mnenc4 anscdf_.h:106) is produced by the lane that owns the coded
-//         symbol and leaves through a 32-record staging line as one coalesced 128-byte store per 16 bytes.
+//         symbol with one predicated 4-byte store (global stores do not order against the shared-memory table traffic,
+//         so the record never sits on the chain).
 //   k_ans_code3   (encoder, coding pass mnflush anscdf_.h:128-138; one LANE per (unit, rANS state): a warp runs 8
 //                  units x 4 states, records popped last to first)
 //       * division by the adaptive frequency is an exact multiply-high with a reciprocal taken from a 32 K-entry table
@@ -22,7 +23,8 @@
 //   k_ans_dec3    (decoder; order 0: one HALF-warp per call, two calls per warp; order 1: one warp per call, both halves
 //                  replicate, 136 KB of tables in the shared memory of one SM)
 //       * symbol search of cdf16ansdec (cdf_.h:52-59) = compare + ballot + popcount; every lane computes the state
-//         update for ITS entry before the symbol is known and one shuffle picks the right one;
+//         update for ITS entry before the symbol is known and one shuffle picks the right one; tables carry the
+//         reference's 17th entry so a lane reads its own and the next entry with two shared loads issued together;
 //       * the stream is staged through a 64-halfword shared-memory ring per call (any byte alignment, refilled one
 //         period ahead), so the four ecdnorm steps (anscdf_.h:50-73) of a byte pair are four speculative 16-bit
 //         shared loads with predicated merges -- no branches in the pair loop.
@@ -40,25 +42,41 @@ constexpr unsigned FULLMASK = 0xffffffffu;
 // encoder, model pass
 // ================================================================================================================
 constexpr int M3_WPB = 4;                                        // warps (units) per CTA, order 0
-constexpr uint32_t M3_STAGE_WORDS = 64;                          // two staging lines of 32 records
-template <bool O1> __host__ __device__ constexpr uint32_t m3_warp_bytes() { return (O1 ? 256u : 1u) * O1_CTX_ENTRIES * 2u + M3_STAGE_WORDS * 4u; }
+template <bool O1> __host__ __device__ constexpr uint32_t m3_warp_bytes() { return (O1 ? 256u : 1u) * O1_CTX_ENTRIES * 2u; }
 
-struct M3State { uint32_t x, off; int m; };                      // current byte, entry offset of its table, this lane's entry
+// Pipeline registers of one lane.  Byte t is being coded; the table entries of bytes t+1 and t+2 are already on their
+// way from shared memory.  `a*` are BYTE offsets of this lane's entry inside the warp's table block.
+struct M3State {
+    uint32_t x0, x1;         // bytes t, t+1 (pre-shifted left by 1: table offsets come out with one AND)
+    uint32_t a0, a1;         // entry address of byte t / t+1
+    uint32_t ap;             // entry address of byte t-1
+    int m;                   // entry value for byte t (up to date)
+    int m2p;                 // value written for byte t-1
+    int pre1;                // entry loaded for byte t+1 (lacks the updates of bytes t-1 and t if they hit the same table)
+    int mp, dnp; bool wp;    // record of byte t-1, still to be stored: entry, next entry (shuffle in flight), "this lane owns it"
+};
 
-// one byte: record of the coded nibble, cdf16upd of this lane's entry, hand-over to the table of the next byte x_n
+__device__ __forceinline__ uint32_t m3_record(int m, int dn, unsigned i) {           // (next - m) | m << 16  (mnenc4 anscdf_.h:106)
+    return (uint32_t)m * 65535u + (uint32_t)(i == 15 ? (int)PROB_TOTAL : dn);
+}
+
+// one byte: cdf16upd of this lane's entry, hand-over to byte t+1, and the record of the PREVIOUS byte (its shuffle was
+// issued a step ago, so nothing waits on it).  x2 = byte t+2 (<< 1); rec_slot = record slot of byte t.
 template <bool O1>
-__device__ __forceinline__ void m3_step(M3State &s, uint32_t x_n, uint16_t *T, uint32_t *stage_slot, unsigned i, unsigned h,
-                                        uint32_t xsh, int c10) {
-    const uint32_t off_n = (O1 ? s.x * (uint32_t)O1_CTX_ENTRIES : 0u) + (h ? 16u + (x_n & 0xf0u) : 0u);   // mbh[cx] / mbl[cx][x_n >> 4]
-    const int pre = T[off_n + i];                                 // stale only if off_n == s.off (forwarded below)
-    const uint32_t xs = (s.x >> xsh) & 15u;
+__device__ __forceinline__ void m3_step(M3State &s, uint32_t x2, uint8_t *Tb, uint32_t *rec_slot, unsigned i, uint32_t hmask, uint32_t xsh,
+                                        int c10, int c10mix) {
+    // table of byte t+2: mbh[cx] (lanes 0-15) / mbl[cx][x >> 4] (lanes 16-31), cx = byte t+1
+    const uint32_t a2 = (O1 ? (s.x1 >> 1) * (uint32_t)(O1_CTX_ENTRIES * 2) : 0u) + (x2 & hmask);
+    const int pre2 = *(const uint16_t *)(Tb + a2);               // issued two bytes ahead of its use
+    const uint32_t xs = (s.x0 >> xsh) & 15u;
     const int dn = __shfl_down_sync(FULLMASK, s.m, 1, 16);
-    const uint32_t f = (uint32_t)((i == 15 ? (int)PROB_TOTAL : dn) - s.m);
-    if (i == xs) *stage_slot = f | (uint32_t)s.m << 16;
-    const int m2 = (127 * s.m + c10 + (i > xs ? (int)AD_MIX : 0)) >> 7;
-    T[s.off + i] = (uint16_t)m2;
-    s.m = off_n == s.off ? m2 : pre;
-    s.off = off_n; s.x = x_n;
+    if (s.wp) rec_slot[-2] = m3_record(s.mp, s.dnp, i);
+    s.mp = s.m; s.dnp = dn; s.wp = i == xs;
+    const int m2 = (127 * s.m + (i > xs ? c10mix : c10)) >> 7;   // cdf16upd
+    *(uint16_t *)(Tb + s.a0) = (uint16_t)m2;
+    const int q1 = s.a1 == s.ap ? s.m2p : s.pre1;                // byte t-1 hit the table of byte t+1
+    s.m = s.a1 == s.a0 ? m2 : q1;                                // byte t did
+    s.m2p = m2; s.ap = s.a0; s.a0 = s.a1; s.a1 = a2; s.pre1 = pre2; s.x0 = s.x1; s.x1 = x2;
 }
 
 template <bool O1>
@@ -68,52 +86,49 @@ k_ans_model3(const uint8_t *__restrict__ in, Geom g, uint32_t *__restrict__ recs
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5, h = lane >> 4, i = lane & 15;
     constexpr uint32_t NENT = (O1 ? 256u : 1u) * O1_CTX_ENTRIES;
     uint16_t *T = (uint16_t *)(smem_raw + (size_t)wib * m3_warp_bytes<O1>());
-    uint32_t *stage = (uint32_t *)(T + NENT);
+    uint8_t *Tb = (uint8_t *)T + (h ? 32u : 0u) + 2u * i;        // this lane's entry of table 0 (high) / table 1 (first low table)
     const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5), gw = (size_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    const int c10 = ADAPT_IC_ * (int)i;
-    const uint32_t xsh = h ? 0u : 4u;
+    const int c10 = ADAPT_IC_ * (int)i, c10mix = c10 + (int)AD_MIX;
+    const uint32_t xsh = h ? 1u : 5u;                            // bytes are kept << 1
+    const uint32_t hmask = h ? 0x1e0u : 0u;                      // (x << 1) & 0x1e0 = 32 * (x >> 4): byte offset of mbl[x >> 4]
     for (size_t u = gw; u < g.n_units; u += nwarps) {
         size_t j, start, len; uint32_t b;
         unit_span(g, u, j, b, start, len);
         if (len == 0) continue;                                   // padding unit: k_ans_code3 writes its (empty) meta
         const uint8_t *ip = in + start;
         const uint32_t n = (uint32_t)len, nb = (n + 1) & ~1u;     // odd tail: a dummy 0 byte is coded too (anscdf.c:581,621)
-        uint32_t *rec = recs + u * rec_stride;
+        uint32_t *rec = recs + u * rec_stride + h;
         __syncwarp();
         for (uint32_t k = lane; k < NENT; k += 32) T[k] = (uint16_t)((k & 15) << 11);   // CDF16DEC0/1/2 cdf_.h:26-32
         __syncwarp();
         const uint32_t cx0 = (O1 && start > j * g.chunk) ? in[start - 1] : 0;           // cx carries across blocks (anscdf.c:608)
-        uint32_t mine = lane < n ? ip[lane] : 0;
+        auto ldb = [&](uint32_t idx) -> uint32_t { return idx < n ? (uint32_t)__ldg(ip + idx) << 1 : 0u; };
+        uint32_t mine = ldb(lane), mine_n = ldb(32 + lane), mine_n2 = ldb(64 + lane);
         M3State s;
-        s.x = __shfl_sync(FULLMASK, mine, 0);
-        s.off = (O1 ? cx0 * (uint32_t)O1_CTX_ENTRIES : 0u) + (h ? 16u + (s.x & 0xf0u) : 0u);
-        s.m = T[s.off + i];
+        s.x0 = __shfl_sync(FULLMASK, mine, 0); s.x1 = __shfl_sync(FULLMASK, mine, 1);
+        s.a0 = (O1 ? cx0 * (uint32_t)(O1_CTX_ENTRIES * 2) : 0u) + (s.x0 & hmask);
+        s.a1 = (O1 ? (s.x0 >> 1) * (uint32_t)(O1_CTX_ENTRIES * 2) : 0u) + (s.x1 & hmask);
+        s.ap = 0xffffffffu; s.m2p = 0; s.mp = s.dnp = 0; s.wp = false;
+        s.m = *(const uint16_t *)(Tb + s.a0);
+        s.pre1 = *(const uint16_t *)(Tb + s.a1);
         for (uint32_t base = 0; base < nb; base += 32) {
-            const uint32_t nidx = base + 32 + lane;
-            const uint32_t mine_n = nidx < n ? ip[nidx] : 0;
+            const uint32_t mine_n3 = ldb(base + 96 + lane);       // three blocks ahead: covers a DRAM miss
             const uint32_t cnt = nb - base < 32 ? nb - base : 32;
             if (cnt == 32) {
 #pragma unroll
                 for (int k = 0; k < 32; k++) {
-                    const uint32_t x_n = k + 1 < 32 ? __shfl_sync(FULLMASK, mine, k + 1) : __shfl_sync(FULLMASK, mine_n, 0);
-                    m3_step<O1>(s, x_n, T, stage + ((k >> 4) & 1) * 32 + 2 * (k & 15) + h, i, h, xsh, c10);
-                    if ((k & 15) == 15) {                          // 16 bytes = 32 records: one 128-byte store
-                        __syncwarp();
-                        rec[2 * (base + (k & ~15)) + lane] = stage[((k >> 4) & 1) * 32 + lane];
-                    }
+                    const uint32_t x2 = k + 2 < 32 ? __shfl_sync(FULLMASK, mine, (k + 2) & 31) : __shfl_sync(FULLMASK, mine_n, (k + 2) & 31);
+                    m3_step<O1>(s, x2, Tb, rec + 2 * (base + k), i, hmask, xsh, c10, c10mix);
                 }
             } else {
-                for (uint32_t k = 0; k < cnt; k++) {
-                    const uint32_t x_n = __shfl_sync(FULLMASK, mine, (k + 1) & 31);       // past the end: any value (prefetch only)
-                    m3_step<O1>(s, x_n, T, stage + ((k >> 4) & 1) * 32 + 2 * (k & 15) + h, i, h, xsh, c10);
-                    if ((k & 15) == 15 || k + 1 == cnt) {
-                        __syncwarp();
-                        if (lane < 2 * ((k & 15) + 1)) rec[2 * (base + (k & ~15u)) + lane] = stage[((k >> 4) & 1) * 32 + lane];
-                    }
+                for (uint32_t k = 0; k < cnt; k++) {              // bytes past the end only feed table prefetches
+                    const uint32_t x2 = __shfl_sync(FULLMASK, mine, (k + 2) & 31);
+                    m3_step<O1>(s, x2, Tb, rec + 2 * (base + k), i, hmask, xsh, c10, c10mix);
                 }
             }
-            mine = mine_n;
+            mine = mine_n; mine_n = mine_n2; mine_n2 = mine_n3;
         }
+        if (s.wp) rec[2 * (nb - 1)] = m3_record(s.mp, s.dnp, i);  // the last byte's record
     }
 }
 
@@ -126,11 +141,21 @@ constexpr uint32_t C3_LUT_BYTES = PROB_TOTAL * 4;                // 128 KB
 
 __device__ uint32_t g_rcp_lut[PROB_TOTAL];                       // [f - 1] = reciprocal of rans_enc_entry(., f), f = 1 .. 2^15
 
+// predicated 16-bit store at p + OFF (kept as ONE predicated instruction: a branch around it costs more than the store)
+__device__ __forceinline__ void st_u16_if(uint8_t *p, int off, uint32_t v, bool pred) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q st.global.u16 [%0 + %1], %2; }" ::"l"(p), "n"(-2), "h"((uint16_t)v), "r"((uint32_t)pred) : "memory");
+    (void)off;
+}
+
 __global__ void k_build_rcp() {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < PROB_TOTAL) g_rcp_lut[k] = rans_enc_entry(0, k + 1).x;
 }
 
+// Frequencies of the adaptive tables never drop below 9: adjacent entries start 2048 apart, their targets are at least
+// IC = 10 apart, and  m' = floor((127 m + T) / 128)  keeps a gap >= 10 (floor(a) - floor(b) >= floor(a - b) =
+// floor((127 d + 10) / 128) >= 10 for d >= 10); the top entry never exceeds 32759.  So the f == 1 special case of
+// rans_enc_entry cannot occur here (tests/test_adaptive_invariants.py replays the argument numerically).
 __global__ void __launch_bounds__(C3_WPB * 32)
 k_ans_code3(Geom g, const uint32_t *__restrict__ recs, size_t rec_stride, uint8_t *__restrict__ slots, size_t slot_stride,
             UnitMeta *__restrict__ meta) {
@@ -149,6 +174,7 @@ k_ans_code3(Geom g, const uint32_t *__restrict__ recs, size_t rec_stride, uint8_
     __syncthreads();
     tma_wait(&bar);
     const unsigned lane = threadIdx.x & 31, k = lane & 3, gb = lane & 28;
+    const unsigned gmask = 15u << gb, lmask = ((1u << k) - 1u) << gb;       // my unit's four lanes / those of lower states
     const size_t gw = (size_t)blockIdx.x * C3_WPB + (threadIdx.x >> 5);
     const size_t u = gw * 8 + (lane >> 2);
     size_t j, start, len = 0; uint32_t blk;
@@ -156,45 +182,61 @@ k_ans_code3(Geom g, const uint32_t *__restrict__ recs, size_t rec_stride, uint8_
     const bool live = len != 0;
     const uint32_t npairs = (uint32_t)((len + 1) >> 1);
     const uint32_t tmax = __reduce_max_sync(FULLMASK, npairs);
+    const uint32_t lead = tmax - npairs;                         // shorter units idle FIRST, so every unit's last step is the warp's last
     const uint32_t *rec = recs + (live ? u : 0) * rec_stride;
     uint8_t *slot = slots + (live ? u : 0) * slot_stride;
     const int cap = (int)slot_stride;
     int pos = cap;                                               // lowest byte written so far (same in the 4 lanes of a unit)
     uint32_t s = ANS_L;
-    bool em = false, ovf = false;
-    // step t codes record 4 (npairs-1-t) + 3 - k on state k (pushed 3,2,1,0 per byte pair -> popped 0,1,2,3)
-    auto ldrec = [&](uint32_t t) -> uint32_t { return t < npairs ? __ldg(rec + 4 * (size_t)(npairs - 1 - t) + 3 - k) : 1u; };
-    uint32_t R[C3_B], Rn[C3_B], Q[C3_B];
+    bool ovf = false, pp = false;                                // pp / pbal / pword: emission of the previous step, still pending
+    unsigned pbal = 0; uint32_t pword = 0;
+    // step t codes record 4 (npairs-1-(t-lead)) + 3 - k on state k (pushed 3,2,1,0 per byte pair -> popped 0,1,2,3).
+    // Idle steps use the record (f = 2^15, cum = 0): it never renormalises and maps every state to itself.
+    auto ldrec = [&](uint32_t t) -> uint32_t { return (t >= lead && t < tmax) ? __ldg(rec + 4 * (size_t)(tmax - 1 - t) + 3 - k) : PROB_TOTAL; };
+    auto ldblock = [&](uint32_t tb, uint32_t (&o)[C3_B]) {      // records of steps tb .. tb+15; whole-block case: one pointer, fixed offsets
+        if (tb >= lead && tb + C3_B <= tmax) {
+            const uint32_t *p = rec + 4 * (size_t)(tmax - 1 - tb) + 3 - k;
 #pragma unroll
-    for (int q = 0; q < C3_B; q++) { R[q] = ldrec(q); Rn[q] = ldrec(C3_B + q); }
+            for (int q = 0; q < C3_B; q++) o[q] = __ldg(p - 4 * q);
+        } else {
+#pragma unroll
+            for (int q = 0; q < C3_B; q++) o[q] = ldrec(tb + q);
+        }
+    };
+    uint32_t R[C3_B], Rn[C3_B], Q[C3_B];
+    ldblock(0, R); ldblock(C3_B, Rn);
 #pragma unroll
     for (int q = 0; q < C3_B; q++) Q[q] = rcp_s[((R[q] & 0xffffu) - 1) & PROB_MASK];
     for (uint32_t t0 = 0; t0 < tmax; t0 += C3_B) {
         uint32_t Rn2[C3_B], Qn[C3_B];
-#pragma unroll
-        for (int q = 0; q < C3_B; q++) Rn2[q] = ldrec(t0 + 2 * C3_B + q);
+        ldblock(t0 + 2 * C3_B, Rn2);
 #pragma unroll
         for (int q = 0; q < C3_B; q++) Qn[q] = rcp_s[((Rn[q] & 0xffffu) - 1) & PROB_MASK];
+        // a block emits at most 16 steps x 4 states x 2 bytes: one slot check per block.  An exhausted slot (the unit is
+        // then certainly raw, see make_plan) restarts at the top so the stores stay inside it.
+        if (pos < 32 + 8 * (C3_B + 1)) { ovf = true; pos = cap; }
 #pragma unroll
         for (int q = 0; q < C3_B; q++) {
-            const bool act = t0 + q < npairs && !ovf;
-            const uint32_t f = R[q] & 0xffffu, c = R[q] >> 16;
-            const uint32_t sh = 31 - __clz((int)((f - 1) | 1));                       // ceil(log2 f) - 1 (0 for f <= 2)
-            const uint32_t bias = c + (f == 1 ? PROB_TOTAL - 1 : 0);                  // rans_enc_entry's f == 1 form
-            const bool p = act && s >= (f << 16);                                     // ecenorm anscdf_.h:48
-            const unsigned grp = (__ballot_sync(FULLMASK, p) >> gb) & 15u;
-            if (p) st_u16(slot + pos - 2 * (__popc(grp & ((1u << k) - 1)) + 1), s);   // state 0's word highest
+            const uint32_t f = R[q] & 0xffffu;
+            const uint32_t sh = 31 - __clz((int)((f - 1) | 1));                       // ceil(log2 f) - 1
+            const bool p = s >= (R[q] << 16);                                         // ecenorm anscdf_.h:48: s >= f << 16
+            const unsigned bal = __ballot_sync(FULLMASK, p);
+            const uint32_t word = s;
             const uint32_t s1 = p ? s >> 16 : s;
             const uint32_t qq = __umulhi(s1, Q[q]) >> sh;                             // == s1 / f
-            const uint32_t sn = s1 + bias + qq * (PROB_TOTAL - f);                    // (q << 15) + s1 % f + cum
-            s = act ? sn : s;
-            pos -= 2 * __popc(grp);
-            em = act ? p : em;
-            ovf = ovf || pos < 32;                                                    // slot exhausted
+            s = s1 + (R[q] >> 16) + qq * (PROB_TOTAL - f);                            // (q << 15) + s1 % f + cum
+            // the word of the PREVIOUS step leaves now: its popcount / address / store chain overlaps this step's state chain
+            st_u16_if(slot + (pos - 2 * (int)__popc(pbal & lmask)), -2, pword, pp);   // state 0's word highest (LIFO of mnflush)
+            pos -= 2 * (int)__popc(pbal & gmask);
+            pbal = bal; pword = word; pp = p;
         }
 #pragma unroll
         for (int q = 0; q < C3_B; q++) { R[q] = Rn[q]; Q[q] = Qn[q]; Rn[q] = Rn2[q]; }
     }
+    st_u16_if(slot + (pos - 2 * (int)__popc(pbal & lmask)), -2, pword, pp);           // the last step's word
+    pos -= 2 * (int)__popc(pbal & gmask);
+    const bool em = pp;
+    if (pos < 32) { ovf = true; pos = cap; }
     if (live) st_u32_a2(slot + pos - 4 * ((int)k + 1), s);                            // ansflush: st[0] highest ... st[3] lowest
     pos -= 16;
     const bool em3 = __shfl_sync(FULLMASK, (int)em, gb | 3);                          // the last-coded record belongs to state 3
@@ -215,8 +257,12 @@ k_ans_code3(Geom g, const uint32_t *__restrict__ recs, size_t rec_stride, uint8_
 constexpr int D3_WPB = 4;                                        // warps per CTA, order 0 (8 calls)
 constexpr uint32_t D3_RING = 64;                                 // halfwords per ring; 4 more mirror the first 4
 constexpr uint32_t D3_RING_BYTES = (D3_RING + 4) * 2;
+// decoder tables carry a 17th entry (= 32768, never written) like the reference's cdf[17], so "the next entry" is a plain
+// shared-memory read issued together with the entry itself instead of a shuffle that has to wait for it
+constexpr uint32_t D3_CTX_ENTRIES = 17 * 17;                     // entries per context: 17 tables x 17 entries
+constexpr uint32_t D3_TAB_BYTES_O0 = (D3_CTX_ENTRIES * 2 + 3) & ~3u;
 template <bool O1> __host__ __device__ constexpr uint32_t d3_smem_bytes() {
-    return O1 ? 256u * O1_CTX_ENTRIES * 2u + 2u * D3_RING_BYTES : D3_WPB * 2u * (O1_CTX_ENTRIES * 2u + D3_RING_BYTES);
+    return O1 ? 256u * D3_CTX_ENTRIES * 2u + 2u * D3_RING_BYTES : D3_WPB * 2u * (D3_TAB_BYTES_O0 + D3_RING_BYTES);
 }
 
 // aligned word with bytes at or past `end` read as zero (never dereferences a word that starts at or past `end`)
@@ -234,17 +280,17 @@ __device__ __forceinline__ uint32_t ld32_any(const uint8_t *p, const uint8_t *en
     return __funnelshift_r(lo, hi, sh);
 }
 
-// one nibble: cdf16ansdec (cdf_.h:52-59) + STATEUPD (cdf_.h:37) + cdf16upd; every lane of the unit returns the same x, s
-__device__ __forceinline__ uint32_t d3_nib(uint32_t &s, int &m, unsigned i, unsigned hb, unsigned hm, int c10) {
+// one nibble: cdf16ansdec (cdf_.h:52-59) + STATEUPD (cdf_.h:37) + cdf16upd; every lane of the unit gets the same result.
+// m / nx = this lane's entry and the next one.  Returns cnt = symbol + 1 (the number of entries <= r); m becomes the updated
+// entry.  hbm1 = (lane & 16) - 1.
+__device__ __forceinline__ uint32_t d3_nib(uint32_t &s, int &m, int nx, unsigned hbm1, unsigned hm, int c10, int c10mix) {
     const uint32_t r = s & PROB_MASK;
     const bool le = (uint32_t)m <= r;                             // entry 0 == 0: always true
-    const int dn = __shfl_down_sync(FULLMASK, m, 1, 16);
-    const uint32_t f = (uint32_t)((i == 15 ? (int)PROB_TOTAL : dn) - m);
-    const uint32_t cand = f * (s >> PROB_BITS) + r - (uint32_t)m; // the new state if this lane's entry is the symbol
-    const unsigned x = __popc(__ballot_sync(FULLMASK, le) & hm) - 1;   // entries are increasing: #(<= r) - 1
-    s = __shfl_sync(FULLMASK, cand, hb | x);
-    m = (127 * m + c10 + (le ? 0 : (int)AD_MIX)) >> 7;            // entry > r  <=>  entry > cdf[x]
-    return x;
+    const uint32_t cand = (uint32_t)(nx - m) * (s >> PROB_BITS) + r - (uint32_t)m;   // the new state if this lane's entry is the symbol
+    const unsigned cnt = __popc(__ballot_sync(FULLMASK, le) & hm);     // entries are increasing: symbol = #(<= r) - 1
+    s = __shfl_sync(FULLMASK, cand, hbm1 + cnt);
+    m = (127 * m + (le ? c10 : c10mix)) >> 7;                     // entry > r  <=>  entry > cdf[x]
+    return cnt;
 }
 
 template <bool O1>
@@ -252,17 +298,18 @@ __global__ void __launch_bounds__(O1 ? 32 : D3_WPB * 32)
 k_ans_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint8_t *__restrict__ out, Geom g) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5, i = lane & 15, hb = lane & 16, half = lane >> 4;
-    constexpr uint32_t NENT = (O1 ? 256u : 1u) * O1_CTX_ENTRIES;
+    constexpr uint32_t NENT = (O1 ? 256u : 1u) * D3_CTX_ENTRIES;
     uint16_t *T, *ring;
     if (O1) { T = (uint16_t *)smem_raw; ring = (uint16_t *)(smem_raw + NENT * 2 + half * D3_RING_BYTES); }
-    else { uint8_t *b = smem_raw + (size_t)(wib * 2 + half) * (NENT * 2 + D3_RING_BYTES); T = (uint16_t *)b; ring = (uint16_t *)(b + NENT * 2); }
+    else { uint8_t *b = smem_raw + (size_t)(wib * 2 + half) * (D3_TAB_BYTES_O0 + D3_RING_BYTES); T = (uint16_t *)b; ring = (uint16_t *)(b + D3_TAB_BYTES_O0); }
     uint32_t *ring32 = (uint32_t *)ring;
-    const unsigned hm = 0xffffu << hb;
-    const int c10 = ADAPT_IC_ * (int)i;
+    const unsigned hm = 0xffffu << hb, hbm1 = hb - 1;
+    const int c10 = ADAPT_IC_ * (int)i, c10mix = c10 + (int)AD_MIX;
     const size_t upw = O1 ? 1 : 2;
     const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5), gw = (size_t)blockIdx.x * (blockDim.x >> 5) + wib;
     const uint8_t *gend = in + in_off[g.n_calls];
-    const bool writer = (O1 ? lane : i) < 2;                      // lanes that store the two bytes of a pair
+    const bool writer = (O1 ? lane : i) < 4;                      // lanes that store the four bytes of two pairs
+    uint16_t *Ti = T + i;                                         // this lane's entry of table 0
     for (size_t jb = gw * upw; jb < g.n_calls; jb += nwarps * upw) {
         const size_t j = jb + (O1 ? 0 : half);
         bool act = j < g.n_calls;
@@ -301,7 +348,7 @@ k_ans_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, 
             const uint32_t np_o = __shfl_xor_sync(FULLMASK, npairs, 16), npmax = npairs > np_o ? npairs : np_o;
             uint8_t *bo = op + bpos;
             __syncwarp();
-            for (uint32_t k = O1 ? lane : i; k < NENT; k += O1 ? 32 : 16) T[k] = (uint16_t)((k & 15) << 11);
+            for (uint32_t k = O1 ? lane : i; k < NENT; k += O1 ? 32 : 16) T[k] = (uint16_t)((k % 17u) << 11);   // CDF16DEC0/1/2 cdf_.h:26-32, entry 16 = 32768
             __syncwarp();
             refill();
             uint32_t s0 = ANS_L, s1 = ANS_L, s2 = ANS_L, s3 = ANS_L;
@@ -310,49 +357,64 @@ k_ans_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, 
                 s0 = hw(0) | hw(1) << 16; s1 = hw(2) | hw(3) << 16; s2 = hw(4) | hw(5) << 16; s3 = hw(6) | hw(7) << 16;
                 hp += 8;
             }
-            int mh = (int)(i << 11);                              // order 0: the high-nibble table never leaves its register
-            for (uint32_t pi = 0; pi < npmax; pi++) {             // mndec8x2 / mndec8x2x anscdf_.h:152-174
-                const bool pact = pi < npairs;
-                refill();
-                uint32_t x0, x1;
-                if (O1) {
-                    const uint32_t c0 = cx * (uint32_t)O1_CTX_ENTRIES + i;
-                    int m = T[c0];
-                    const uint32_t yh0 = d3_nib(s0, m, i, hb, hm, c10); T[c0] = (uint16_t)m;
-                    const uint32_t l0 = c0 + (1 + yh0) * 16;
-                    m = T[l0];
-                    const uint32_t yl0 = d3_nib(s1, m, i, hb, hm, c10); T[l0] = (uint16_t)m;
-                    x0 = yh0 << 4 | yl0;
-                    const uint32_t c1 = x0 * (uint32_t)O1_CTX_ENTRIES + i;
-                    m = T[c1];
-                    const uint32_t yh1 = d3_nib(s2, m, i, hb, hm, c10); T[c1] = (uint16_t)m;
-                    const uint32_t l1 = c1 + (1 + yh1) * 16;
-                    m = T[l1];
-                    const uint32_t yl1 = d3_nib(s3, m, i, hb, hm, c10); T[l1] = (uint16_t)m;
-                    x1 = yh1 << 4 | yl1;
-                    cx = x1;
-                } else {
-                    const uint32_t yh0 = d3_nib(s0, mh, i, hb, hm, c10);
-                    const uint32_t l0 = (1 + yh0) * 16 + i;
-                    int m = T[l0];
-                    const uint32_t yl0 = d3_nib(s1, m, i, hb, hm, c10); T[l0] = (uint16_t)m;
-                    x0 = yh0 << 4 | yl0;
-                    const uint32_t yh1 = d3_nib(s2, mh, i, hb, hm, c10);
-                    const uint32_t l1 = (1 + yh1) * 16 + i;
-                    m = T[l1];
-                    const uint32_t yl1 = d3_nib(s3, m, i, hb, hm, c10); T[l1] = (uint16_t)m;
-                    x1 = yh1 << 4 | yl1;
+            int mh = (int)(i << 11), mhn = (int)((i + 1) << 11);  // order 0: the high-nibble table (entry, next entry) stays in registers
+            auto nib_h0 = [&](uint32_t &st) -> uint32_t {         // order 0 high nibble: update, then fetch the neighbour's new entry for the NEXT use
+                const uint32_t c = d3_nib(st, mh, mhn, hbm1, hm, c10, c10mix);
+                const int dn = __shfl_down_sync(FULLMASK, mh, 1, 16);
+                mhn = i == 15 ? (int)PROB_TOTAL : dn;
+                return c;
+            };
+            auto nib_t = [&](uint32_t &st, uint16_t *e) -> uint32_t {   // table in shared memory
+                int m = e[0], nx;
+                if (O1) {                                         // one warp alone on its SM: latency is everything, so the next entry
+                    nx = e[1];                                    // is read with the entry itself (it is the neighbour lane's e[0]:
+                    __syncwarp();                                 // every read precedes every write ...
+                } else {                                          // many warps: the shuffle costs less than the ordering constraints
+                    const int dn = __shfl_down_sync(FULLMASK, m, 1, 16);
+                    nx = i == 15 ? (int)PROB_TOTAL : dn;
                 }
-                // ecdnorm x4 in state order (anscdf_.h:158-161): speculative 16-bit ring reads, predicated merges
-                const uint16_t *rp = ring + (hp & (D3_RING - 1));
-                uint32_t cnt = 0;
-                { const bool p = pact && s0 < ANS_L; const uint32_t v = rp[cnt]; s0 = p ? (s0 << 16 | v) : s0; cnt += p; }
-                { const bool p = pact && s1 < ANS_L; const uint32_t v = rp[cnt]; s1 = p ? (s1 << 16 | v) : s1; cnt += p; }
-                { const bool p = pact && s2 < ANS_L; const uint32_t v = rp[cnt]; s2 = p ? (s2 << 16 | v) : s2; cnt += p; }
-                { const bool p = pact && s3 < ANS_L; const uint32_t v = rp[cnt]; s3 = p ? (s3 << 16 | v) : s3; cnt += p; }
-                hp += cnt;
-                const uint32_t o = 2 * pi + (lane & 1);
-                if (pact && writer && o < n) bo[o] = (uint8_t)((lane & 1) ? x1 : x0);   // odd tail: second byte discarded (anscdf.c:602)
+                const uint32_t c = d3_nib(st, m, nx, hbm1, hm, c10, c10mix);
+                e[0] = (uint16_t)m;
+                if (O1) __syncwarp();                             // ... and every write the table's next use)
+                return c;
+            };
+            for (uint32_t pi = 0; pi < npmax; pi += 2) {          // two byte pairs per trip (mndec8x2 / mndec8x2x anscdf_.h:152-174)
+                refill();                                         // <= 8 halfwords are consumed per trip, >= 32 are staged after this
+                uint32_t w = 0;                                   // the four decoded bytes
+#pragma unroll
+                for (int sub = 0; sub < 2; sub++) {
+                    const bool pact = pi + sub < npairs;
+                    uint32_t x0, x1;
+                    if (O1) {
+                        uint16_t *c0 = Ti + cx * D3_CTX_ENTRIES;
+                        const uint32_t h0 = nib_t(s0, c0);
+                        const uint32_t q0 = nib_t(s1, c0 + h0 * 17);
+                        x0 = h0 * 16 + q0 - 17;
+                        uint16_t *c1 = Ti + x0 * D3_CTX_ENTRIES;
+                        const uint32_t h1 = nib_t(s2, c1);
+                        const uint32_t q1 = nib_t(s3, c1 + h1 * 17);
+                        x1 = h1 * 16 + q1 - 17;
+                        cx = x1;
+                    } else {
+                        const uint32_t h0 = nib_h0(s0);
+                        const uint32_t q0 = nib_t(s1, Ti + h0 * 17);
+                        x0 = h0 * 16 + q0 - 17;
+                        const uint32_t h1 = nib_h0(s2);
+                        const uint32_t q1 = nib_t(s3, Ti + h1 * 17);
+                        x1 = h1 * 16 + q1 - 17;
+                    }
+                    // ecdnorm x4 in state order (anscdf_.h:158-161): speculative 16-bit ring reads, predicated merges
+                    const uint16_t *rp = ring + (hp & (D3_RING - 1));
+                    uint32_t cnt = 0;
+                    { const bool p = pact && s0 < ANS_L; const uint32_t v = rp[cnt]; s0 = p ? (s0 << 16 | v) : s0; cnt += p; }
+                    { const bool p = pact && s1 < ANS_L; const uint32_t v = rp[cnt]; s1 = p ? (s1 << 16 | v) : s1; cnt += p; }
+                    { const bool p = pact && s2 < ANS_L; const uint32_t v = rp[cnt]; s2 = p ? (s2 << 16 | v) : s2; cnt += p; }
+                    { const bool p = pact && s3 < ANS_L; const uint32_t v = rp[cnt]; s3 = p ? (s3 << 16 | v) : s3; cnt += p; }
+                    hp += cnt;
+                    w |= (x0 | x1 << 8) << (16 * sub);
+                }
+                const uint32_t o = 2 * pi + (lane & 3);
+                if (writer && o < n) bo[o] = (uint8_t)(w >> (8 * (lane & 3)));   // o < n also drops the odd tail's second byte (anscdf.c:602)
             }
         }
     }
