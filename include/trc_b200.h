@@ -110,6 +110,28 @@ int trc_dec_batch_host(int codec, const unsigned char *in, const uint64_t *in_of
 int trc_cdfini_batch_dev(const unsigned char *d_in, size_t total_len, size_t chunk_len,
                          cdf_t *d_cdf, unsigned cdfnum, int *d_status, void *cuda_stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Self-describing container.  The reference's codec calls carry no lengths, tables
+ * or cdfnum -- bench() keeps them on the side (turborc.c:423-433) and file mode wraps every block in a
+ * { block size, inlen, clen } header with clen == inlen meaning "stored" (turborc.c:665-733, 1123).  The
+ * container gathers those per-block headers into one directory in front of the payload (a GPU decodes all
+ * blocks at once), computes the static tables on the device (cdfini, rccdf.c:50-68) and ships them along:
+ *
+ *   [64-byte header: "TRCB", version, codec, total_len, chunk_len, cdf_block, n_chunks, n_tables, cdfnum, payload_bytes]
+ *   [n_tables x 257 cdf_t]  [n_chunks x u32 compressed length (== input length: raw copy)]  [payload]
+ *
+ * payload == the packed stream of trc_enc_batch_*: chunk c is byte-for-byte one call of the codec's reference
+ * encoder.  cdf_block: bytes of input per static table (0 = one table for the buffer; must be a multiple of
+ * chunk_len); cdfnum is 256 (16 for TRC_ANS4S).  This format is this library's own: the reference has no
+ * counterpart at this level, so it is round-trip tested, and its payload is checked against the oracle.
+ * ------------------------------------------------------------------------------------------------------ */
+size_t trc_container_bound(int codec, size_t total_len, size_t chunk_len, size_t cdf_block);
+int trc_compress_host(int codec, const unsigned char *in, size_t total_len, size_t chunk_len, size_t cdf_block,
+                      unsigned char *out, size_t out_cap, size_t *out_len);
+int trc_decompress_host(const unsigned char *in, size_t in_len, unsigned char *out, size_t out_cap, size_t *out_len);
+/* host-only header check; any of the out pointers may be NULL */
+int trc_container_info(const unsigned char *in, size_t in_len, int *codec, size_t *total_len, size_t *chunk_len, size_t *n_chunks);
+
 /* Multi-GPU gather over peer memory (one process per GPU): the destination rank allocates a buffer, exports a
  * CUDA-IPC handle, the other ranks open it and push their packed streams straight into it with a kernel whose byte
  * count is read from device memory (the encoder's out_off[n]) -- no host round trip, no collective call. */

@@ -144,6 +144,50 @@ def dec_batch_host(codec, stream, off, total_len, chunk_len, cdf=None, cdfnum=0,
 
 
 # ----------------------------------------------------------------------------------------------------------
+# self-describing container (include/trc_b200.h): tables computed on the GPU, directory + payload in one buffer
+# ----------------------------------------------------------------------------------------------------------
+lib.trc_container_bound.restype = _sz; lib.trc_container_bound.argtypes = [_i, _sz, _sz, _sz]
+lib.trc_compress_host.restype = _i; lib.trc_compress_host.argtypes = [_i, _vp, _sz, _sz, _sz, _vp, _sz, _vp]
+lib.trc_decompress_host.restype = _i; lib.trc_decompress_host.argtypes = [_vp, _sz, _vp, _sz, _vp]
+lib.trc_container_info.restype = _i; lib.trc_container_info.argtypes = [_vp, _sz, _vp, _vp, _vp, _vp]
+CONTAINER_HEADER = 64
+
+
+def compress(codec, data, chunk_len, cdf_block=0):
+    """-> container bytes (header, static tables made by the GPU's cdfini, per-chunk lengths, packed reference streams)"""
+    data = _u8(data)
+    cap = int(lib.trc_container_bound(codec, data.size, chunk_len, cdf_block))
+    if cap == 0:
+        raise TrcError("trc_container_bound: bad arguments")
+    out = np.empty(cap, np.uint8)
+    olen = ctypes.c_size_t(0)
+    _check(lib.trc_compress_host(codec, data.ctypes.data, data.size, chunk_len, cdf_block, out.ctypes.data, cap, ctypes.addressof(olen)),
+           "trc_compress_host")
+    return out[:olen.value]
+
+
+def container_info(blob):
+    """-> dict(codec, total_len, chunk_len, n_chunks); raises TrcError on a malformed header (host only, no GPU)"""
+    blob = _u8(blob)
+    codec = ctypes.c_int(0)
+    tl, cl, n = ctypes.c_size_t(0), ctypes.c_size_t(0), ctypes.c_size_t(0)
+    rc = lib.trc_container_info(blob.ctypes.data if blob.size else None, blob.size, ctypes.addressof(codec), ctypes.addressof(tl),
+                                ctypes.addressof(cl), ctypes.addressof(n))
+    if rc != OK:
+        raise TrcError(f"trc_container_info failed ({rc}): not a TRCB container")
+    return {"codec": codec.value, "total_len": tl.value, "chunk_len": cl.value, "n_chunks": n.value}
+
+
+def decompress(blob):
+    blob = _u8(blob)
+    info = container_info(blob)
+    out = np.empty(info["total_len"], np.uint8)
+    olen = ctypes.c_size_t(0)
+    _check(lib.trc_decompress_host(blob.ctypes.data, blob.size, out.ctypes.data, out.size, ctypes.addressof(olen)), "trc_decompress_host")
+    return out[:olen.value]
+
+
+# ----------------------------------------------------------------------------------------------------------
 # batch layer, device pointers (torch tensors only carry the memory and the stream)
 # ----------------------------------------------------------------------------------------------------------
 class DeviceBatch:

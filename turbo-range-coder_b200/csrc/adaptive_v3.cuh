@@ -102,8 +102,10 @@ k_ans_model3(const uint8_t *__restrict__ in, Geom g, uint32_t *__restrict__ recs
         for (uint32_t k = lane; k < NENT; k += 32) T[k] = (uint16_t)((k & 15) << 11);   // CDF16DEC0/1/2 cdf_.h:26-32
         __syncwarp();
         const uint32_t cx0 = (O1 && start > j * g.chunk) ? in[start - 1] : 0;           // cx carries across blocks (anscdf.c:608)
-        auto ldb = [&](uint32_t idx) -> uint32_t { return idx < n ? (uint32_t)__ldg(ip + idx) << 1 : 0u; };
-        uint32_t mine = ldb(lane), mine_n = ldb(32 + lane), mine_n2 = ldb(64 + lane);
+        // input bytes: one per lane and 32-byte block, loaded three blocks ahead; the << 1 is applied a block before use so
+        // that nothing touches a register a DRAM load is still filling
+        auto ldb = [&](uint32_t idx) -> uint32_t { return idx < n ? (uint32_t)__ldg(ip + idx) : 0u; };
+        uint32_t mine = ldb(lane) << 1, mine_n = ldb(32 + lane) << 1, mine_n2 = ldb(64 + lane);
         M3State s;
         s.x0 = __shfl_sync(FULLMASK, mine, 0); s.x1 = __shfl_sync(FULLMASK, mine, 1);
         s.a0 = (O1 ? cx0 * (uint32_t)(O1_CTX_ENTRIES * 2) : 0u) + (s.x0 & hmask);
@@ -126,7 +128,7 @@ k_ans_model3(const uint8_t *__restrict__ in, Geom g, uint32_t *__restrict__ recs
                     m3_step<O1>(s, x2, Tb, rec + 2 * (base + k), i, hmask, xsh, c10, c10mix);
                 }
             }
-            mine = mine_n; mine_n = mine_n2; mine_n2 = mine_n3;
+            mine = mine_n; mine_n = mine_n2 << 1; mine_n2 = mine_n3;
         }
         if (s.wp) rec[2 * (nb - 1)] = m3_record(s.mp, s.dnp, i);  // the last byte's record
     }
@@ -203,15 +205,17 @@ k_ans_code3(Geom g, const uint32_t *__restrict__ recs, size_t rec_stride, uint8_
             for (int q = 0; q < C3_B; q++) o[q] = ldrec(tb + q);
         }
     };
-    uint32_t R[C3_B], Rn[C3_B], Q[C3_B];
-    ldblock(0, R); ldblock(C3_B, Rn);
+    // Records and reciprocals travel through three register blocks whose roles rotate (A = being coded, B = next, its
+    // reciprocals being fetched, C = being loaded), written out three times so that no register that a load is still
+    // filling is ever moved; further ahead, the record lines are pulled into L2 by prefetches.
+    auto prefetch = [&](uint32_t tb) {
+        if (tb >= lead && tb < tmax) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 4 * (size_t)(tmax - 1 - tb) + 3 - k));
+    };
+    auto lut = [&](const uint32_t (&r)[C3_B], uint32_t (&q)[C3_B]) {
 #pragma unroll
-    for (int q = 0; q < C3_B; q++) Q[q] = rcp_s[((R[q] & 0xffffu) - 1) & PROB_MASK];
-    for (uint32_t t0 = 0; t0 < tmax; t0 += C3_B) {
-        uint32_t Rn2[C3_B], Qn[C3_B];
-        ldblock(t0 + 2 * C3_B, Rn2);
-#pragma unroll
-        for (int q = 0; q < C3_B; q++) Qn[q] = rcp_s[((Rn[q] & 0xffffu) - 1) & PROB_MASK];
+        for (int x = 0; x < C3_B; x++) q[x] = rcp_s[((r[x] & 0xffffu) - 1) & PROB_MASK];
+    };
+    auto code_block = [&](const uint32_t (&R)[C3_B], const uint32_t (&Q)[C3_B]) {
         // a block emits at most 16 steps x 4 states x 2 bytes: one slot check per block.  An exhausted slot (the unit is
         // then certainly raw, see make_plan) restarts at the top so the stores stay inside it.
         if (pos < 32 + 8 * (C3_B + 1)) { ovf = true; pos = cap; }
@@ -230,8 +234,17 @@ k_ans_code3(Geom g, const uint32_t *__restrict__ recs, size_t rec_stride, uint8_
             pos -= 2 * (int)__popc(pbal & gmask);
             pbal = bal; pword = word; pp = p;
         }
-#pragma unroll
-        for (int q = 0; q < C3_B; q++) { R[q] = Rn[q]; Q[q] = Qn[q]; Rn[q] = Rn2[q]; }
+    };
+    uint32_t R0[C3_B], R1[C3_B], R2[C3_B], Q0[C3_B], Q1[C3_B], Q2[C3_B];
+    ldblock(0, R0); ldblock(C3_B, R1);
+    for (uint32_t tb = 2 * C3_B; tb < 8 * C3_B; tb += C3_B) prefetch(tb);
+    lut(R0, Q0);
+    for (uint32_t t0 = 0; t0 < tmax;) {
+        ldblock(t0 + 2 * C3_B, R2); prefetch(t0 + 8 * C3_B); lut(R1, Q1); code_block(R0, Q0); t0 += C3_B;
+        if (t0 >= tmax) break;
+        ldblock(t0 + 2 * C3_B, R0); prefetch(t0 + 8 * C3_B); lut(R2, Q2); code_block(R1, Q1); t0 += C3_B;
+        if (t0 >= tmax) break;
+        ldblock(t0 + 2 * C3_B, R1); prefetch(t0 + 8 * C3_B); lut(R0, Q0); code_block(R2, Q2); t0 += C3_B;
     }
     st_u16_if(slot + (pos - 2 * (int)__popc(pbal & lmask)), -2, pword, pp);           // the last step's word
     pos -= 2 * (int)__popc(pbal & gmask);
@@ -257,12 +270,12 @@ k_ans_code3(Geom g, const uint32_t *__restrict__ recs, size_t rec_stride, uint8_
 constexpr int D3_WPB = 4;                                        // warps per CTA, order 0 (8 calls)
 constexpr uint32_t D3_RING = 64;                                 // halfwords per ring; 4 more mirror the first 4
 constexpr uint32_t D3_RING_BYTES = (D3_RING + 4) * 2;
-// decoder tables carry a 17th entry (= 32768, never written) like the reference's cdf[17], so "the next entry" is a plain
-// shared-memory read issued together with the entry itself instead of a shuffle that has to wait for it
-constexpr uint32_t D3_CTX_ENTRIES = 17 * 17;                     // entries per context: 17 tables x 17 entries
-constexpr uint32_t D3_TAB_BYTES_O0 = (D3_CTX_ENTRIES * 2 + 3) & ~3u;
+// order-1 decoder tables carry a 17th entry (= 32768, never written) like the reference's cdf[17], so "the next entry" is a
+// plain shared-memory read issued together with the entry itself instead of a shuffle that has to wait for it
+template <bool O1> __host__ __device__ constexpr uint32_t d3_stride() { return O1 ? 17u : 16u; }              // entries per table
+template <bool O1> __host__ __device__ constexpr uint32_t d3_ctx_entries() { return 17u * d3_stride<O1>(); }  // 17 tables per context
 template <bool O1> __host__ __device__ constexpr uint32_t d3_smem_bytes() {
-    return O1 ? 256u * D3_CTX_ENTRIES * 2u + 2u * D3_RING_BYTES : D3_WPB * 2u * (D3_TAB_BYTES_O0 + D3_RING_BYTES);
+    return O1 ? 256u * d3_ctx_entries<true>() * 2u + 2u * D3_RING_BYTES : D3_WPB * 2u * (d3_ctx_entries<false>() * 2u + D3_RING_BYTES);
 }
 
 // aligned word with bytes at or past `end` read as zero (never dereferences a word that starts at or past `end`)
@@ -298,10 +311,10 @@ __global__ void __launch_bounds__(O1 ? 32 : D3_WPB * 32)
 k_ans_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint8_t *__restrict__ out, Geom g) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5, i = lane & 15, hb = lane & 16, half = lane >> 4;
-    constexpr uint32_t NENT = (O1 ? 256u : 1u) * D3_CTX_ENTRIES;
+    constexpr uint32_t STR = d3_stride<O1>(), CTX = d3_ctx_entries<O1>(), NENT = (O1 ? 256u : 1u) * CTX;
     uint16_t *T, *ring;
     if (O1) { T = (uint16_t *)smem_raw; ring = (uint16_t *)(smem_raw + NENT * 2 + half * D3_RING_BYTES); }
-    else { uint8_t *b = smem_raw + (size_t)(wib * 2 + half) * (D3_TAB_BYTES_O0 + D3_RING_BYTES); T = (uint16_t *)b; ring = (uint16_t *)(b + D3_TAB_BYTES_O0); }
+    else { uint8_t *b = smem_raw + (size_t)(wib * 2 + half) * (NENT * 2 + D3_RING_BYTES); T = (uint16_t *)b; ring = (uint16_t *)(b + NENT * 2); }
     uint32_t *ring32 = (uint32_t *)ring;
     const unsigned hm = 0xffffu << hb, hbm1 = hb - 1;
     const int c10 = ADAPT_IC_ * (int)i, c10mix = c10 + (int)AD_MIX;
@@ -348,7 +361,7 @@ k_ans_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, 
             const uint32_t np_o = __shfl_xor_sync(FULLMASK, npairs, 16), npmax = npairs > np_o ? npairs : np_o;
             uint8_t *bo = op + bpos;
             __syncwarp();
-            for (uint32_t k = O1 ? lane : i; k < NENT; k += O1 ? 32 : 16) T[k] = (uint16_t)((k % 17u) << 11);   // CDF16DEC0/1/2 cdf_.h:26-32, entry 16 = 32768
+            for (uint32_t k = O1 ? lane : i; k < NENT; k += O1 ? 32 : 16) T[k] = (uint16_t)((k % STR) << 11);   // CDF16DEC0/1/2 cdf_.h:26-32 (order 1: entry 16 = 32768)
             __syncwarp();
             refill();
             uint32_t s0 = ANS_L, s1 = ANS_L, s2 = ANS_L, s3 = ANS_L;
@@ -357,25 +370,25 @@ k_ans_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, 
                 s0 = hw(0) | hw(1) << 16; s1 = hw(2) | hw(3) << 16; s2 = hw(4) | hw(5) << 16; s3 = hw(6) | hw(7) << 16;
                 hp += 8;
             }
-            int mh = (int)(i << 11), mhn = (int)((i + 1) << 11);  // order 0: the high-nibble table (entry, next entry) stays in registers
-            auto nib_h0 = [&](uint32_t &st) -> uint32_t {         // order 0 high nibble: update, then fetch the neighbour's new entry for the NEXT use
-                const uint32_t c = d3_nib(st, mh, mhn, hbm1, hm, c10, c10mix);
-                const int dn = __shfl_down_sync(FULLMASK, mh, 1, 16);
-                mhn = i == 15 ? (int)PROB_TOTAL : dn;
-                return c;
+            int mh = (int)(i << 11);                              // order 0: the high-nibble table never leaves its register
+            auto nib_r = [&](uint32_t &st, int &m) -> uint32_t {  // next entry by shuffle (measured faster than any hoisting of it)
+                const int dn = __shfl_down_sync(FULLMASK, m, 1, 16);
+                return d3_nib(st, m, i == 15 ? (int)PROB_TOTAL : dn, hbm1, hm, c10, c10mix);
             };
+            auto nib_h0 = [&](uint32_t &st) -> uint32_t { return nib_r(st, mh); };
             auto nib_t = [&](uint32_t &st, uint16_t *e) -> uint32_t {   // table in shared memory
-                int m = e[0], nx;
+                int m = e[0];
+                uint32_t c;
                 if (O1) {                                         // one warp alone on its SM: latency is everything, so the next entry
-                    nx = e[1];                                    // is read with the entry itself (it is the neighbour lane's e[0]:
-                    __syncwarp();                                 // every read precedes every write ...
-                } else {                                          // many warps: the shuffle costs less than the ordering constraints
-                    const int dn = __shfl_down_sync(FULLMASK, m, 1, 16);
-                    nx = i == 15 ? (int)PROB_TOTAL : dn;
+                    const int nx = e[1];                          // is read together with the entry itself.  It is the neighbour
+                    __syncwarp();                                 // lane's e[0]: every read precedes every write ...
+                    c = d3_nib(st, m, nx, hbm1, hm, c10, c10mix);
+                    e[0] = (uint16_t)m;
+                    __syncwarp();                                 // ... and every write the table's next use
+                } else {
+                    c = nib_r(st, m);
+                    e[0] = (uint16_t)m;
                 }
-                const uint32_t c = d3_nib(st, m, nx, hbm1, hm, c10, c10mix);
-                e[0] = (uint16_t)m;
-                if (O1) __syncwarp();                             // ... and every write the table's next use)
                 return c;
             };
             for (uint32_t pi = 0; pi < npmax; pi += 2) {          // two byte pairs per trip (mndec8x2 / mndec8x2x anscdf_.h:152-174)
@@ -386,21 +399,21 @@ k_ans_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, 
                     const bool pact = pi + sub < npairs;
                     uint32_t x0, x1;
                     if (O1) {
-                        uint16_t *c0 = Ti + cx * D3_CTX_ENTRIES;
+                        uint16_t *c0 = Ti + cx * CTX;
                         const uint32_t h0 = nib_t(s0, c0);
-                        const uint32_t q0 = nib_t(s1, c0 + h0 * 17);
+                        const uint32_t q0 = nib_t(s1, c0 + h0 * STR);
                         x0 = h0 * 16 + q0 - 17;
-                        uint16_t *c1 = Ti + x0 * D3_CTX_ENTRIES;
+                        uint16_t *c1 = Ti + x0 * CTX;
                         const uint32_t h1 = nib_t(s2, c1);
-                        const uint32_t q1 = nib_t(s3, c1 + h1 * 17);
+                        const uint32_t q1 = nib_t(s3, c1 + h1 * STR);
                         x1 = h1 * 16 + q1 - 17;
                         cx = x1;
                     } else {
                         const uint32_t h0 = nib_h0(s0);
-                        const uint32_t q0 = nib_t(s1, Ti + h0 * 17);
+                        const uint32_t q0 = nib_t(s1, Ti + h0 * STR);
                         x0 = h0 * 16 + q0 - 17;
                         const uint32_t h1 = nib_h0(s2);
-                        const uint32_t q1 = nib_t(s3, Ti + h1 * 17);
+                        const uint32_t q1 = nib_t(s3, Ti + h1 * STR);
                         x1 = h1 * 16 + q1 - 17;
                     }
                     // ecdnorm x4 in state order (anscdf_.h:158-161): speculative 16-bit ring reads, predicated merges

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 #include <chrono>
 
 using namespace trc;
@@ -635,6 +636,139 @@ int trc_dec_batch_host(int codec, const unsigned char *in, const uint64_t *in_of
     if (!in || !in_off || !out || !chunk_len) return TRC_E_ARG;
     size_t n = trc_num_chunks(total_len, chunk_len);
     return host_dec(codec, in, in_off, (size_t)in_off[n], out, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, flags);
+}
+
+// ---- self-describing container ---------------------------------------------------------
+// The reference's codec calls carry no lengths, tables or cdfnum: bench() keeps them on the side, and file mode wraps each
+// block in a header of { block size, inlen, clen } with clen == inlen meaning "stored" (turborc.c:665-733, 1123).  The
+// container keeps that idea but gathers the per-block headers into ONE directory in front of the payload, because a GPU
+// decodes every block at once and needs all offsets before the first byte.  Static tables are computed on the device
+// (cdfini semantics, rccdf.c:50-68) and travel in the container.  Payload = the batch layer's packed stream, i.e. every
+// chunk is still byte-for-byte one reference call.
+namespace {
+constexpr uint32_t CT_MAGIC = 0x42435254u;                         // "TRCB"
+constexpr size_t   CT_HDR = 64;
+struct CtHeader {
+    uint32_t magic; uint16_t version; uint8_t codec, flags;
+    uint64_t total_len, chunk_len, cdf_block, n_chunks;
+    uint32_t n_tables, cdfnum;
+    uint64_t payload_bytes, reserved;
+};
+static_assert(sizeof(CtHeader) == CT_HDR, "container header is 64 bytes");
+static inline size_t al8(size_t x) { return (x + 7) & ~(size_t)7; }
+struct CtLayout { size_t n, ntab, cpc, off_tabs, off_dir, off_payload; unsigned cdfnum; };
+
+int ct_layout(int codec, size_t total_len, size_t chunk_len, size_t cdf_block, CtLayout &L) {
+    if (codec < 0 || codec >= NCODECS || total_len == 0 || chunk_len == 0) return TRC_E_ARG;
+    L.n = (total_len + chunk_len - 1) / chunk_len;
+    L.cpc = 0; L.ntab = 0; L.cdfnum = 0;
+    if (codec_static(codec)) {
+        if (cdf_block && cdf_block % chunk_len) return TRC_E_ARG;  // a table covers whole chunks
+        L.cpc = cdf_block ? cdf_block / chunk_len : 0;
+        L.ntab = n_tables(L.n, L.cpc);
+        L.cdfnum = codec == ANS4S ? 16 : 256;
+    }
+    L.off_tabs = CT_HDR;
+    L.off_dir = L.off_tabs + al8(L.ntab * CDF_STRIDE * sizeof(cdf_t));
+    L.off_payload = al16(L.off_dir + L.n * sizeof(uint32_t));
+    return TRC_OK;
+}
+}  // namespace
+
+size_t trc_container_bound(int codec, size_t total_len, size_t chunk_len, size_t cdf_block) {
+    CtLayout L; if (ct_layout(codec, total_len, chunk_len, cdf_block, L) != TRC_OK) return 0;
+    return L.off_payload + trc_enc_bound(total_len, chunk_len);
+}
+
+int trc_container_info(const unsigned char *in, size_t in_len, int *codec, size_t *total_len, size_t *chunk_len, size_t *n_chunks) {
+    if (!in || in_len < CT_HDR) return TRC_E_ARG;
+    CtHeader h; memcpy(&h, in, CT_HDR);
+    if (h.magic != CT_MAGIC || h.version != 1 || h.codec >= NCODECS || h.total_len == 0 || h.chunk_len == 0) return TRC_E_ARG;
+    CtLayout L; if (ct_layout(h.codec, h.total_len, h.chunk_len, h.cdf_block, L) != TRC_OK) return TRC_E_ARG;
+    if (h.n_chunks != L.n || h.n_tables != L.ntab || h.cdfnum != L.cdfnum) return TRC_E_ARG;
+    if (L.off_payload > in_len || h.payload_bytes > in_len - L.off_payload) return TRC_E_ARG;
+    if (codec) *codec = h.codec;
+    if (total_len) *total_len = (size_t)h.total_len;
+    if (chunk_len) *chunk_len = (size_t)h.chunk_len;
+    if (n_chunks) *n_chunks = (size_t)h.n_chunks;
+    return TRC_OK;
+}
+
+int trc_compress_host(int codec, const unsigned char *in, size_t total_len, size_t chunk_len, size_t cdf_block,
+                      unsigned char *out, size_t out_cap, size_t *out_len) {
+    if (!in || !out) return TRC_E_ARG;
+    CtLayout L; int rc = ct_layout(codec, total_len, chunk_len, cdf_block, L); if (rc) return rc;
+    if (out_cap < L.off_payload + trc_enc_bound(total_len, chunk_len)) return TRC_E_NOMEM;
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    Ctx &c = g_ctx;
+    if ((rc = c.ensure())) return rc;
+    Plan p; if ((rc = make_plan(codec, total_len, chunk_len, p))) return rc;
+    if ((rc = c.in.need(total_len + 64)) || (rc = c.out.need(trc_enc_bound(total_len, chunk_len))) || (rc = c.off.need((L.n + 1) * 8)) ||
+        (rc = c.scratch.need(p.total + 256)) || (rc = c.cdf.need((L.ntab + 1) * CDF_STRIDE * sizeof(cdf_t))) || (rc = c.status.need((L.ntab + 1) * sizeof(int)))) return rc;
+    CK(cudaMemcpyAsync(c.in.p, in, total_len, cudaMemcpyHostToDevice, c.st));
+    if (L.ntab) {                                                  // tables on the device, one per cdf_block bytes
+        rc = trc_cdfini_batch_dev((const unsigned char *)c.in.p, total_len, cdf_block ? cdf_block : total_len, (cdf_t *)c.cdf.p, L.cdfnum, (int *)c.status.p, c.st);
+        if (rc) return rc;
+    }
+    rc = trc_enc_batch_dev(codec, (const unsigned char *)c.in.p, total_len, chunk_len, (const cdf_t *)c.cdf.p, L.cdfnum, L.cpc,
+                           (unsigned char *)c.out.p, (uint64_t *)c.off.p, c.scratch.p, c.scratch.cap, c.st);
+    if (rc) return rc;
+    std::vector<uint64_t> off(L.n + 1);
+    std::vector<int> status(L.ntab);
+    CK(cudaMemcpyAsync(off.data(), c.off.p, (L.n + 1) * 8, cudaMemcpyDeviceToHost, c.st));
+    if (L.ntab) {
+        CK(cudaMemcpyAsync(status.data(), c.status.p, L.ntab * sizeof(int), cudaMemcpyDeviceToHost, c.st));
+        CK(cudaMemcpyAsync(out + L.off_tabs, c.cdf.p, L.ntab * CDF_STRIDE * sizeof(cdf_t), cudaMemcpyDeviceToHost, c.st));
+    }
+    CK(cudaStreamSynchronize(c.st));
+    for (int sct : status) if (sct) { snprintf(g_err, sizeof g_err, "cdfini: degenerate table (the reference would die(), rccdf.c:65)"); return TRC_E_ARG; }
+    const uint64_t payload = off[L.n];
+    CK(cudaMemcpyAsync(out + L.off_payload, c.out.p, payload, cudaMemcpyDeviceToHost, c.st));
+    CtHeader h; memset(&h, 0, sizeof h);
+    h.magic = CT_MAGIC; h.version = 1; h.codec = (uint8_t)codec; h.total_len = total_len; h.chunk_len = chunk_len; h.cdf_block = cdf_block;
+    h.n_chunks = L.n; h.n_tables = (uint32_t)L.ntab; h.cdfnum = L.cdfnum; h.payload_bytes = payload;
+    memcpy(out, &h, CT_HDR);
+    memset(out + L.off_tabs + L.ntab * CDF_STRIDE * sizeof(cdf_t), 0, L.off_dir - (L.off_tabs + L.ntab * CDF_STRIDE * sizeof(cdf_t)));
+    uint32_t *dir = (uint32_t *)(out + L.off_dir);                 // clen per chunk; == the chunk's input length -> stored raw
+    for (size_t k = 0; k < L.n; k++) dir[k] = (uint32_t)(off[k + 1] - off[k]);
+    memset(out + L.off_dir + L.n * 4, 0, L.off_payload - (L.off_dir + L.n * 4));
+    CK(cudaStreamSynchronize(c.st));
+    if (out_len) *out_len = L.off_payload + (size_t)payload;
+    return TRC_OK;
+}
+
+int trc_decompress_host(const unsigned char *in, size_t in_len, unsigned char *out, size_t out_cap, size_t *out_len) {
+    int codec; size_t total_len, chunk_len, n;
+    int rc = trc_container_info(in, in_len, &codec, &total_len, &chunk_len, &n); if (rc) return rc;
+    if (!out || out_cap < total_len) return TRC_E_NOMEM;
+    CtHeader h; memcpy(&h, in, CT_HDR);
+    CtLayout L; ct_layout(codec, total_len, chunk_len, h.cdf_block, L);
+    std::vector<uint64_t> off(n + 1);
+    const unsigned char *dirp = in + L.off_dir;
+    off[0] = 0;
+    for (size_t k = 0; k < n; k++) {
+        uint32_t cl; memcpy(&cl, dirp + 4 * k, 4);
+        const size_t ilen = k + 1 < n ? chunk_len : total_len - k * chunk_len;
+        if (cl > ilen + 4) return TRC_E_ARG;                        // (+4: rccdf4ienc's answer on inputs shorter than 4 bytes)
+        off[k + 1] = off[k] + cl;
+    }
+    if (off[n] != h.payload_bytes) return TRC_E_ARG;
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    Ctx &c = g_ctx;
+    if ((rc = c.ensure())) return rc;
+    if ((rc = c.in.need((size_t)h.payload_bytes + 64)) || (rc = c.out.need(total_len + 64)) || (rc = c.off.need((n + 1) * 8)) ||
+        (rc = c.cdf.need((L.ntab + 1) * CDF_STRIDE * sizeof(cdf_t)))) return rc;
+    CK(cudaMemcpyAsync(c.off.p, off.data(), (n + 1) * 8, cudaMemcpyHostToDevice, c.st));
+    CK(cudaMemcpyAsync(c.in.p, in + L.off_payload, (size_t)h.payload_bytes, cudaMemcpyHostToDevice, c.st));
+    CK(cudaMemsetAsync((uint8_t *)c.in.p + h.payload_bytes, 0, 64, c.st));
+    if (L.ntab) CK(cudaMemcpyAsync(c.cdf.p, in + L.off_tabs, L.ntab * CDF_STRIDE * sizeof(cdf_t), cudaMemcpyHostToDevice, c.st));
+    rc = trc_dec_batch_dev(codec, (const unsigned char *)c.in.p, (const uint64_t *)c.off.p, (unsigned char *)c.out.p, total_len, chunk_len,
+                           (const cdf_t *)c.cdf.p, L.cdfnum, L.cpc, 0, c.st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, c.out.p, total_len, cudaMemcpyDeviceToHost, c.st));
+    CK(cudaStreamSynchronize(c.st));                                // `off` must outlive the upload
+    if (out_len) *out_len = total_len;
+    return TRC_OK;
 }
 
 // ---- drop-in layer ----------------------------------------------------------------------------------------
