@@ -332,8 +332,11 @@ def run_ours(args):
     achieved = alg / (kern_ms[dom] * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp) and size == 100_000_000 and chunk == 4096 and args.src == "zipf":   # the capture is of this exact workload
-        traffic = json.load(open(tp)).get(f"{args.codec}/{dom}")
+    if os.path.exists(tp) and size == 100_000_000:                       # captures are of exact workloads (100 MB)
+        tj = json.load(open(tp))
+        traffic = tj.get(f"{args.codec}/{dom}@{chunk}/{args.src}")
+        if traffic is None and chunk == 4096 and args.src == "zipf":
+            traffic = tj.get(f"{args.codec}/{dom}")
     roofline = {"bound": "hbm", "kernel": f"{args.codec}/{dom}", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(alg), "kernel_ms": kern_ms}
