@@ -22,6 +22,8 @@ size_t rccdfenc(unsigned char *, size_t, unsigned char *), rccdfdec(unsigned cha
 size_t rccdf4enc(unsigned char *, size_t, unsigned char *), rccdf4dec(unsigned char *, size_t, unsigned char *);
 size_t rccdfienc(unsigned char *, size_t, unsigned char *), rccdfidec(unsigned char *, size_t, unsigned char *);
 size_t rccdf4ienc(unsigned char *, size_t, unsigned char *), rccdf4idec(unsigned char *, size_t, unsigned char *);
+size_t rccdfenc8(unsigned char *, size_t, unsigned char *), rccdfdec8(unsigned char *, size_t, unsigned char *);
+size_t rccdfienc8(unsigned char *, size_t, unsigned char *), rccdfidec8(unsigned char *, size_t, unsigned char *);
 size_t anscdfenc(unsigned char *, size_t, unsigned char *), anscdfdec(unsigned char *, size_t, unsigned char *);
 size_t anscdf4enc(unsigned char *, size_t, unsigned char *), anscdf4dec(unsigned char *, size_t, unsigned char *);
 size_t anscdf1enc(unsigned char *, size_t, unsigned char *), anscdf1dec(unsigned char *, size_t, unsigned char *);
@@ -50,6 +52,8 @@ int main(int argc, char **argv) {
     case 45: l = rccdfs2enc(in, n, out, cdf, m + 1); CCPY(m < 16 ? rccdfsl2dec(out, n, cpy, cdf, m + 1) : rccdfsb2dec(out, n, cpy, cdf, m + 1)); break;
     case 46: if (m < 16) { l = rccdf4enc(in, n, out); CCPY(rccdf4dec(out, n, cpy)); } else { l = rccdfenc(in, n, out); CCPY(rccdfdec(out, n, cpy)); } break;
     case 47: if (m < 16) { l = rccdf4ienc(in, n, out); CCPY(rccdf4idec(out, n, cpy)); } else { l = rccdfienc(in, n, out); CCPY(rccdfidec(out, n, cpy)); } break;
+    case 48: l = rccdfenc8(in, n, out);  CCPY(rccdfdec8(out, n, cpy)); break;                                      /* turborc.c:503 */
+    case 49: l = rccdfienc8(in, n, out); CCPY(rccdfidec8(out, n, cpy)); break;                                     /* turborc.c:504 */
     case 56: if (m < 16) { l = anscdf4enc(in, n, out); CCPY(anscdf4dec(out, n, cpy)); } else { l = anscdfenc(in, n, out); CCPY(anscdfdec(out, n, cpy)); } break;
     case 64: l = anscdf1enc(in, n, out); CCPY(anscdf1dec(out, n, cpy)); break;
     case 65: if (m < 16) { l = anscdf4senc(in, n, out, cdf); CCPY(anscdf4sdec(out, n, cpy, cdf)); } break;

@@ -16,6 +16,10 @@
       TM("94:gpu ans    o1, batch                  ", l = xtrc_enc(TRC_ANS1, in, n, ck, out, NULL, 0),  n, l, xtrc_dec(TRC_ANS1, out, n, ck, cpy, NULL, 0)); } break;
     case 95: { size_t ck = xtrc_chunk(65536);
       TM("95:gpu cdfi   byte adaptive interlv,batch", l = xtrc_enc(TRC_RCI,  in, n, ck, out, NULL, 0),  n, l, xtrc_dec(TRC_RCI,  out, n, ck, cpy, NULL, 0)); } break;
+    case 98: { size_t ck = xtrc_chunk(4096);
+      TM("98:gpu cdf-8  vnibble, batch             ", l = xtrc_enc(TRC_RC8,  in, n, ck, out, NULL, 0),  n, l, xtrc_dec(TRC_RC8,  out, n, ck, cpy, NULL, 0)); } break;
+    case 99: { size_t ck = xtrc_chunk(4096);
+      TM("99:gpu cdfi-8 vnibble interleaved, batch ", l = xtrc_enc(TRC_RCI8, in, n, ck, out, NULL, 0),  n, l, xtrc_dec(TRC_RCI8, out, n, ck, cpy, NULL, 0)); } break;
     case 96: { XTRC_CDF(); xtrc_f5 e = (xtrc_f5)xtrc_sym("rccdfs2enc"), d = (xtrc_f5)xtrc_sym("rccdfsb2dec");
       TM("96:gpu cdfsb  static interlv, drop-in    ", l = e(in, n, out, cdf, m+1), n, l, CCPY:d(out, n, cpy, cdf, m+1)); } break;
     case 97: { xtrc_f3 e = (xtrc_f3)xtrc_sym("anscdfenc"), d = (xtrc_f3)xtrc_sym("anscdfdec");

@@ -14,6 +14,8 @@
  *   95   TRC_RCI   rccdfienc  / rccdfidec,   64 KiB chunks              47
  *   96   drop-in symbol rccdfs2enc / rccdfsb2dec of libtrc_b200.so (whole buffer == one call; same bytes as id 45)
  *   97   drop-in symbol anscdfenc / anscdfdec    of libtrc_b200.so (whole buffer; same bytes as id 56)
+ *   98   TRC_RC8   rccdfenc8  / rccdfdec8,   4 KiB chunks               48
+ *   99   TRC_RCI8  rccdfienc8 / rccdfidec8,  4 KiB chunks               49
  * Chunk sizes can be overridden with the environment variable TRC_CHUNK (bytes).
  */
 #ifndef XTURBORC_H_

@@ -44,7 +44,9 @@ enum trc_codec {
     TRC_ANSW  = 10, /* NOT a reference format: 32-way warp-interleaved static rANS, one state per lane, one stream per call
                        (the layout BASELINE's north star describes).  Parity unpinned: oracle/trc_oracle.c orc_answenc/dec is
                        the specification.  Static table like TRC_ANS4S; chunk_len must be a multiple of 4. */
-    TRC_NCODECS = 11
+    TRC_RC8   = 11, /* [f.3]   rccdfenc8   / rccdfdec8    adaptive RC over the vnibble byte code   rccdf.c:324-351  */
+    TRC_RCI8  = 12, /* [f.3]   rccdfienc8  / rccdfidec8   same, 2 coders                           rccdf.c:354-389  */
+    TRC_NCODECS = 13
 };
 
 #define TRC_CDF_STRIDE 257                    /* entries per static table (cdf_t cdf[0x100+1], turborc.c:423) */
@@ -188,6 +190,10 @@ size_t rccdf4enc  (unsigned char *in, size_t inlen,  unsigned char *out);       
 size_t rccdf4dec  (unsigned char *in, size_t outlen, unsigned char *out);                                  /* rccdf.c:251 */
 size_t rccdf4ienc (unsigned char *in, size_t inlen,  unsigned char *out);                                  /* rccdf.c:302 */
 size_t rccdf4idec (unsigned char *in, size_t outlen, unsigned char *out);                                  /* rccdf.c:280 */
+size_t rccdfenc8  (unsigned char *in, size_t inlen,  unsigned char *out);                                  /* rccdf.c:341 */
+size_t rccdfdec8  (unsigned char *in, size_t outlen, unsigned char *out);                                  /* rccdf.c:324 */
+size_t rccdfienc8 (unsigned char *in, size_t inlen,  unsigned char *out);                                  /* rccdf.c:371 */
+size_t rccdfidec8 (unsigned char *in, size_t outlen, unsigned char *out);                                  /* rccdf.c:354 */
 
 #ifdef __cplusplus
 }

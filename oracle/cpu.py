@@ -26,7 +26,7 @@ ENCODERS = {
     "anscdf4senc": (True, False), "anscdf4enc": (False, False), "anscdfenc": (False, False),
     "anscdf1enc": (False, False), "rccdfsenc": (True, True), "rccdfs2enc": (True, True),
     "rccdfenc": (False, False), "rccdfienc": (False, False), "rccdf4enc": (False, False),
-    "rccdf4ienc": (False, False),
+    "rccdf4ienc": (False, False), "rccdfenc8": (False, False), "rccdfienc8": (False, False),
     "answenc": (True, True),      # port-only: this repository's 32-way interleaved static rANS (parity unpinned)
 }
 DECODERS = {
@@ -34,7 +34,7 @@ DECODERS = {
     "anscdf1dec": (False, False), "rccdfsbdec": (True, True), "rccdfsb2dec": (True, True),
     "rccdfsldec": (True, True), "rccdfsl2dec": (True, True),
     "rccdfdec": (False, False), "rccdfidec": (False, False), "rccdf4dec": (False, False),
-    "rccdf4idec": (False, False),
+    "rccdf4idec": (False, False), "rccdfdec8": (False, False), "rccdfidec8": (False, False),
     # port-only (no reference counterpart): true inverses with the tail state fixed / wide alphabet
     "ans_sdec_n": (True, True), "anscdf4dec_fix": (False, False), "answdec": (True, True),
 }
@@ -42,7 +42,7 @@ PAIRS = {  # encoder -> decoder the reference harness pairs it with (turborc.c:4
     "anscdf4senc": "anscdf4sdec", "anscdf4enc": "anscdf4dec", "anscdfenc": "anscdfdec",
     "anscdf1enc": "anscdf1dec", "rccdfsenc": "rccdfsbdec", "rccdfs2enc": "rccdfsb2dec",
     "rccdfenc": "rccdfdec", "rccdfienc": "rccdfidec", "rccdf4enc": "rccdf4dec",
-    "rccdf4ienc": "rccdf4idec",
+    "rccdf4ienc": "rccdf4idec", "rccdfenc8": "rccdfdec8", "rccdfienc8": "rccdfidec8",
 }
 
 

@@ -487,6 +487,64 @@ size_t orc_rccdfidec(const uint8_t *in, size_t outlen, uint8_t *out) {          
     return outlen;
 }
 
+/* V8: "vnibble" byte code, rccdfenc8 / rccdfdec8 / rccdfienc8 / rccdfidec8 (rccdf.c:324-389) over cdfe8 / cdfd8
+ * (rccdf_.h:76-96): x < 13 -> one symbol on table 0; x < 45 -> (x-13 >> 4) + 13 on table 0, low nibble on table 1;
+ * else 15 on table 0, (x-45) >> 4 on table 1, low nibble on table 2.  The interleaved form puts the table-1 symbols
+ * on coder 1 and everything else on coder 0. */
+static void rce_v8(rcenc *e0, rcenc *e1, cdf_t *m0, cdf_t *m1, cdf_t *m2, unsigned x) {
+    if (x < 13) rce_nib(e0, m0, x);
+    else if (x < 13 + 32) { x -= 13; rce_nib(e0, m0, (x >> 4) + 13); rce_nib(e1, m1, x & 15); }
+    else { x -= 13 + 32; rce_nib(e0, m0, 15); rce_nib(e1, m1, x >> 4); rce_nib(e0, m2, x & 15); }
+}
+static unsigned rcd_v8(rcdec *d0, rcdec *d1, cdf_t *m0, cdf_t *m1, cdf_t *m2) {
+    unsigned x = rcd_nib(d0, m0);
+    if (x >= 13) {
+        unsigned y = rcd_nib(d1, m1);
+        if (x != 15) x = ((x - 13) << 4 | y) + 13;
+        else { x = rcd_nib(d0, m2); x = (y << 4 | x) + 13 + 32; }
+    }
+    return x;
+}
+size_t orc_rccdfenc8(const uint8_t *in, size_t inlen, uint8_t *out) {                 /* rccdf.c:341-351 */
+    cdf_t m0[17], m1[17], m2[17]; adapt_init(m0); adapt_init(m1); adapt_init(m2);
+    rcenc e; rce_init(&e, out);
+    for (size_t i = 0; i < inlen; i++) {
+        rce_v8(&e, &e, m0, m1, m2, in[i]);
+        if (rc_overflow(e.op, out, inlen)) { memcpy(out, in, inlen); return inlen; }
+    }
+    rce_flush(&e);
+    return (size_t)(e.op - out);
+}
+size_t orc_rccdfdec8(const uint8_t *in, size_t outlen, uint8_t *out) {                /* rccdf.c:324-339 */
+    cdf_t m0[17], m1[17], m2[17]; adapt_init(m0); adapt_init(m1); adapt_init(m2);
+    rcdec d; rcd_init(&d, in);
+    for (size_t i = 0; i < outlen; i++) out[i] = (uint8_t)rcd_v8(&d, &d, m0, m1, m2);
+    return outlen;
+}
+size_t orc_rccdfienc8(const uint8_t *in, size_t inlen, uint8_t *out) {                /* rccdf.c:371-389 */
+    cdf_t m0[17], m1[17], m2[17]; adapt_init(m0); adapt_init(m1); adapt_init(m2);
+    uint8_t *base0 = out + 4, *base1 = out + 4 + inlen * 37 / 64;
+    rcenc e0, e1; rce_init(&e0, base0); rce_init(&e1, base1);
+    size_t i = 0;
+    for (; i < (inlen & ~(size_t)3); i += 4) {
+        for (int k = 0; k < 4; k++) rce_v8(&e0, &e1, m0, m1, m2, in[i + k]);
+        if (rc_overflow(e1.op, out, inlen) || e0.op >= base1) { memcpy(out, in, inlen); return inlen; }   /* OVERFLOWI rccdf.c:46 */
+    }
+    for (; i < inlen; i++) rce_v8(&e0, &e1, m0, m1, m2, in[i]);
+    rce_flush(&e0); rce_flush(&e1);
+    st32(out, (uint32_t)(e0.op - base0));
+    size_t l1 = (size_t)(e1.op - base1);
+    memmove(e0.op, base1, l1); e0.op += l1;
+    if (rc_overflow(e0.op, out, inlen)) { memcpy(out, in, inlen); return inlen; }
+    return (size_t)(e0.op - out);
+}
+size_t orc_rccdfidec8(const uint8_t *in, size_t outlen, uint8_t *out) {               /* rccdf.c:354-369 */
+    cdf_t m0[17], m1[17], m2[17]; adapt_init(m0); adapt_init(m1); adapt_init(m2);
+    rcdec d0, d1; rcd_init(&d0, in + 4); rcd_init(&d1, in + 4 + ld32(in));
+    for (size_t i = 0; i < outlen; i++) out[i] = (uint8_t)rcd_v8(&d0, &d1, m0, m1, m2);
+    return outlen;
+}
+
 /* R11: nibble-alphabet adaptive RC (rccdf.c:251-323) */
 size_t orc_rccdf4enc(const uint8_t *in, size_t inlen, uint8_t *out) {
     cdf_t t[17]; adapt_init(t);

@@ -13,6 +13,8 @@ CODECS = {
     7: ("rccdfienc", "rccdfidec", False, False),
     8: ("rccdf4enc", "rccdf4dec", False, True),
     9: ("rccdf4ienc", "rccdf4idec", False, True),
+    11: ("rccdfenc8", "rccdfdec8", False, False),      # vnibble; id 10 is TRC_ANSW (own format, own test)
+    12: ("rccdfienc8", "rccdfidec8", False, False),
 }
 
 

@@ -19,12 +19,12 @@ def test_demo_binaries_link():
     out = subprocess.run(["ldd", GPU_BIN], capture_output=True, text=True).stdout
     assert "libtrc_b200.so" in out and "not found" not in out, out
     nm = subprocess.run(["nm", "-D", "--undefined-only", GPU_BIN], capture_output=True, text=True).stdout
-    for sym in ("cdfini", "rccdfs2enc", "rccdfsb2dec", "anscdfenc", "anscdfdec", "anscdf1enc", "anscdf4senc", "rccdfienc"):
+    for sym in ("cdfini", "rccdfs2enc", "rccdfsb2dec", "anscdfenc", "anscdfdec", "anscdf1enc", "anscdf4senc", "rccdfienc", "rccdfenc8", "rccdfidec8"):
         assert sym in nm
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("ident", [42, 45, 46, 47, 56, 64, 65])
+@pytest.mark.parametrize("ident", [42, 45, 46, 47, 48, 49, 56, 64, 65])
 def test_same_source_same_bytes(tmp_path, ident):
     if not os.path.exists(REF_BIN):
         pytest.skip("host/_build/dropin_demo_ref not built (needs oracle/_ref)")

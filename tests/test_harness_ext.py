@@ -54,7 +54,7 @@ def test_harness_gpu_rows(tmp_path, dg, port):
         pytest.skip("oracle/_ref/turborc_gpu not built")
     from helpers import cpu_batch
     n = 3_000_001
-    cases = {"zipf": (dg.zipf(n), "45,90,91,96,56,92,97,46,93,47,95"), "o1": (dg.markov1(n), "64,94")}
+    cases = {"zipf": (dg.zipf(n), "45,90,91,96,56,92,97,46,93,47,95,48,98,49,99"), "o1": (dg.markov1(n), "64,94")}
     for name, (data, ids) in cases.items():
         src = tmp_path / f"{name}.bin"
         data.tofile(src)
@@ -67,7 +67,7 @@ def test_harness_gpu_rows(tmp_path, dg, port):
             assert rows[96] == rows[45] and rows[97] == rows[56]                  # drop-in symbols: the reference's own sizes
             cdf = port.cdfini(data)
             num = int(data.max()) + 1
-            for ident, codec, chunk in ((90, 5, 4096), (91, 4, 4096), (92, 2, 65536), (93, 6, 65536), (95, 7, 65536)):   # ids of helpers.CODECS
+            for ident, codec, chunk in ((90, 5, 4096), (91, 4, 4096), (92, 2, 65536), (93, 6, 65536), (95, 7, 65536), (98, 11, 4096), (99, 12, 4096)):   # ids of helpers.CODECS
                 _, off = cpu_batch(port, codec, data, chunk, cdf if codec in (4, 5) else None, num if codec in (4, 5) else 0)
                 assert rows[ident] == int(off[-1]), (ident, rows[ident], int(off[-1]))
         else:

@@ -17,14 +17,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtrc_b200.so")
 
 # enum trc_codec (include/trc_b200.h)
-ANS4S, ANS4, ANS, ANS1, RCS, RCS2, RC, RCI, RC4, RC4I, ANSW = range(11)
-CODEC_NAMES = ["ANS4S", "ANS4", "ANS", "ANS1", "RCS", "RCS2", "RC", "RCI", "RC4", "RC4I", "ANSW"]
+ANS4S, ANS4, ANS, ANS1, RCS, RCS2, RC, RCI, RC4, RC4I, ANSW, RC8, RCI8 = range(13)
+CODEC_NAMES = ["ANS4S", "ANS4", "ANS", "ANS1", "RCS", "RCS2", "RC", "RCI", "RC4", "RC4I", "ANSW", "RC8", "RCI8"]
 #: codec id -> (reference encoder, reference decoder)
 REF_NAMES = {
     ANS4S: ("anscdf4senc", "anscdf4sdec"), ANS4: ("anscdf4enc", "anscdf4dec"), ANS: ("anscdfenc", "anscdfdec"),
     ANS1: ("anscdf1enc", "anscdf1dec"), RCS: ("rccdfsenc", "rccdfsbdec"), RCS2: ("rccdfs2enc", "rccdfsb2dec"),
     RC: ("rccdfenc", "rccdfdec"), RCI: ("rccdfienc", "rccdfidec"), RC4: ("rccdf4enc", "rccdf4dec"),
-    RC4I: ("rccdf4ienc", "rccdf4idec"),
+    RC4I: ("rccdf4ienc", "rccdf4idec"), RC8: ("rccdfenc8", "rccdfdec8"), RCI8: ("rccdfienc8", "rccdfidec8"),
 }
 STATIC = (ANS4S, RCS, RCS2, ANSW)
 F_REF_TAIL = 1
@@ -252,9 +252,9 @@ def cdfini_dev(d_in, total_len, chunk_len, cdfnum=256):
 # ----------------------------------------------------------------------------------------------------------
 # drop-in layer: the reference's own names (host buffers, whole-buffer calls)
 # ----------------------------------------------------------------------------------------------------------
-_ENC3 = ["anscdf4enc", "anscdfenc", "anscdf1enc", "rccdfenc", "rccdfienc", "rccdf4enc", "rccdf4ienc",
+_ENC3 = ["anscdf4enc", "anscdfenc", "anscdf1enc", "rccdfenc", "rccdfienc", "rccdf4enc", "rccdf4ienc", "rccdfenc8", "rccdfienc8",
          "anscdf4encs", "anscdf4encx", "anscdfencs", "anscdfencx", "anscdf1encs", "anscdf1encx"]
-_DEC3 = ["anscdf4dec", "anscdfdec", "anscdf1dec", "rccdfdec", "rccdfidec", "rccdf4dec", "rccdf4idec",
+_DEC3 = ["anscdf4dec", "anscdfdec", "anscdf1dec", "rccdfdec", "rccdfidec", "rccdf4dec", "rccdf4idec", "rccdfdec8", "rccdfidec8",
          "anscdf4decs", "anscdf4decx", "anscdfdecs", "anscdfdecx", "anscdf1decs", "anscdf1decx"]
 _ENC4 = ["anscdf4senc", "anscdf4sencs", "anscdf4sencx"]
 _DEC4 = ["anscdf4sdec", "anscdf4sdecs", "anscdf4sdecx"]

@@ -8,6 +8,7 @@
 #include "static_v2.cuh"
 #include "adaptive_coop.cuh"
 #include "adaptive_v3.cuh"
+#include "vnibble.cuh"
 #include "rans_wide.cuh"
 #include "pack.cuh"
 #include <cstdio>
@@ -233,6 +234,8 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
                 else k_rc_byte_enc_coop<2><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, g, slots, p.slot_stride, meta, g_force_redo); break;
     case RC4:   k_rc_adapt_enc<R_NIB1, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
     case RC4I:  k_rc_adapt_enc<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
+    case RC8:   k_rc_v8_enc<1><<<blocks(g.n_calls, V8_NT), V8_NT, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
+    case RCI8:  k_rc_v8_enc<2><<<blocks(g.n_calls, V8_NT), V8_NT, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
     }
     CK_LAUNCH(); prof_mark(st);
     k_resolve<<<blocks(g.n_calls, 256), 256, 0, st>>>(g, codec_blocked(codec) ? 1 : 0, meta, calls);
@@ -317,6 +320,8 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
                 else k_rc_byte_dec_coop<2><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, d_in_off, d_out, g); break;
     case RC4:   k_rc_adapt_dec<R_NIB1, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
     case RC4I:  k_rc_adapt_dec<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
+    case RC8:   k_rc_v8_dec<1><<<blocks(g.n_calls, V8_NT), V8_NT, 0, st>>>(d_in, d_in_off, d_out, g); break;
+    case RCI8:  k_rc_v8_dec<2><<<blocks(g.n_calls, V8_NT), V8_NT, 0, st>>>(d_in, d_in_off, d_out, g); break;
     }
     CK_LAUNCH(); prof_mark(st);
     return TRC_OK;
@@ -596,7 +601,7 @@ size_t dropin_enc(const char *fn, int codec, unsigned char *in, size_t inlen, un
     if (inlen == 0) {
         // reference on an empty buffer: the rANS codecs write nothing; a single range coder still flushes one
         // word (low += 2^32 -> 0x00000001, turborc_.h:120-122); the 2-coder forms dereference wild pointers.
-        if (codec == RCS || codec == RC || codec == RC4) { uint32_t one = 1; memcpy(out, &one, 4); return 4; }
+        if (codec == RCS || codec == RC || codec == RC4 || codec == RC8) { uint32_t one = 1; memcpy(out, &one, 4); return 4; }
         return 0;
     }
     size_t l = 0;
@@ -791,6 +796,8 @@ ENC3(rccdfenc, RC) DEC3(rccdfdec, RC, 0)
 ENC3(rccdfienc, RCI) DEC3(rccdfidec, RCI, 0)
 ENC3(rccdf4enc, RC4) DEC3(rccdf4dec, RC4, 0)
 ENC3(rccdf4ienc, RC4I) DEC3(rccdf4idec, RC4I, 0)
+ENC3(rccdfenc8, RC8) DEC3(rccdfdec8, RC8, 0)
+ENC3(rccdfienc8, RCI8) DEC3(rccdfidec8, RCI8, 0)
 
 #define ENC5(name, codec) size_t name(unsigned char *in, size_t inlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum) { return dropin_enc(#name, codec, in, inlen, out, cdf, cdfnum); }
 #define DEC5(name, codec) size_t name(unsigned char *in, size_t outlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum) { return dropin_dec(#name, codec, in, outlen, out, cdf, cdfnum, 0); }
