@@ -60,7 +60,9 @@ static void lpc_shape(size_t n_calls, size_t cpc, unsigned &calls_per_cta, unsig
     if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
     calls_per_cta = LPC_NT / 2;
     const size_t per_sm = (n_calls + n_sm - 1) / n_sm;
-    if (cpc == 0 && per_sm > LPC_NT / 2 && per_sm <= LPC_MAX_NT / 2) calls_per_cta = (unsigned)per_sm;
+    // one wave of equally loaded CTAs: k CTAs per SM (k <= 3 keeps registers and the 33 KB tables of each CTA resident)
+    const size_t k = (per_sm + LPC_MAX_NT / 2 - 1) / (LPC_MAX_NT / 2);
+    if (cpc == 0 && per_sm > LPC_NT / 2 && k >= 1 && k <= 3) calls_per_cta = (unsigned)((n_calls + (size_t)n_sm * k - 1) / ((size_t)n_sm * k));
     ctas = (unsigned)((n_calls + calls_per_cta - 1) / calls_per_cta);
 }
 // lane-per-call v2 kernels: threads per CTA (one call per thread), same balancing idea
