@@ -433,4 +433,126 @@ k_ans_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, 
     }
 }
 
+// ================================================================================================================
+// adaptive byte RANGE decoders TRC_RC (rccdfdec rccdf.c:187-200) and TRC_RCI (rccdfidec rccdf.c:213-228), same mapping as
+// k_ans_dec3<false>: one HALF-warp per call, one CDF entry per lane, the high-nibble table in a register.
+//   * _cdflget16 (turborc_.h:271-291: first entry with cdf[e+1] * range > code) = one 47 x 15-bit multiply-compare per lane +
+//     ballot + popcount;
+//   * every lane prepares the coder update for ITS entry -- code - cdf[e] * range and range * (cdf[e+1] - cdf[e])
+//     (_rccdfupdate turborc_.h:219-229) -- before the symbol is known; four shuffles fetch the winner's;
+//   * the stream is staged through a 32-word shared-memory ring per coder (any byte alignment, refilled one period ahead);
+//     the renormalisation is one speculative 32-bit shared load + selects, no branch.
+// NC == 2: coder 0 decodes the high nibbles, coder 1 the low nibbles (cdf8d2 rccdf_.h:63-73), two rings.
+// ================================================================================================================
+constexpr uint32_t R3_RING = 32;                                 // 32-bit words per ring
+template <int NC> __host__ __device__ constexpr uint32_t r3_smem_bytes() { return D3_WPB * 2u * (O1_CTX_ENTRIES * 2u + NC * R3_RING * 4u); }
+
+struct Rc3 {                                                     // range decoder state, replicated in the 16 lanes of a call
+    uint32_t rl, rh, cl, ch;                                     // range, code
+    uint32_t wp, wf, pend;                                       // words consumed / staged; this lane's word of [wf, wf+16)
+    uint32_t *ring; const uint8_t *sp;
+};
+
+// one nibble; m = this lane's entry (updated on return).  Returns cnt = symbol + 1.
+__device__ __forceinline__ uint32_t r3_nib(Rc3 &d, int &m, unsigned i, unsigned hbm1, unsigned hm, int c10, int c10mix) {
+    const int dn = __shfl_down_sync(FULLMASK, m, 1, 16);
+    const uint32_t f = (uint32_t)((i == 15 ? (int)PROB_TOTAL : dn) - m), mu = (uint32_t)m;
+    const uint32_t rl = __funnelshift_r(d.rl, d.rh, PROB_BITS), rh = d.rh >> PROB_BITS;     // range >>= 15
+    const uint32_t pl = mu * rl, ph = __umulhi(mu, rl) + mu * rh;                           // cdf[e] * range
+    const bool le = ph < d.ch || (ph == d.ch && pl <= d.cl);                                  // entry 0 == 0: always true
+    uint32_t dl, dh;
+    asm("sub.cc.u32 %0, %2, %4;\n\tsubc.u32 %1, %3, %5;" : "=r"(dl), "=r"(dh) : "r"(d.cl), "r"(d.ch), "r"(pl), "r"(ph));
+    const uint32_t nl = rl * f, nh = __umulhi(rl, f) + rh * f;                              // range * freq
+    const unsigned cnt = __popc(__ballot_sync(FULLMASK, le) & hm), src = hbm1 + cnt;
+    const uint32_t xdl = __shfl_sync(FULLMASK, dl, src), xdh = __shfl_sync(FULLMASK, dh, src);
+    const uint32_t xnl = __shfl_sync(FULLMASK, nl, src), xnh = __shfl_sync(FULLMASK, nh, src);
+    const uint32_t w = d.ring[d.wp & (R3_RING - 1)];                                          // speculative: used iff the range dropped below 2^32
+    const bool p = xnh == 0;                                                                  // _rcdnorm_ turborc_.h:111
+    d.rh = p ? xnl : xnh; d.rl = p ? 0u : xnl;
+    d.ch = p ? xdl : xdh; d.cl = p ? w : xdl;
+    d.wp += p;
+    m = (127 * m + (le ? c10 : c10mix)) >> 7;                                                 // cdf16upd
+    return cnt;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(D3_WPB * 32)
+k_rc_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint8_t *__restrict__ out, Geom g) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5, i = lane & 15, hb = lane & 16, half = lane >> 4;
+    uint8_t *blk = smem_raw + (size_t)(wib * 2 + half) * (O1_CTX_ENTRIES * 2u + NC * R3_RING * 4u);
+    uint16_t *T = (uint16_t *)blk, *Ti = T + i;
+    uint32_t *rings = (uint32_t *)(blk + O1_CTX_ENTRIES * 2u);
+    const unsigned hm = 0xffffu << hb, hbm1 = hb - 1;
+    const int c10 = ADAPT_IC_ * (int)i, c10mix = c10 + (int)AD_MIX;
+    const size_t nwarps = (size_t)gridDim.x * (blockDim.x >> 5), gw = (size_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    const uint8_t *gend = in + in_off[g.n_calls];
+    const bool writer = i < 4;
+    for (size_t jb = gw * 2; jb < g.n_calls; jb += nwarps * 2) {
+        const size_t j = jb + half;
+        bool act = j < g.n_calls;
+        size_t start = 0, n = 0; uint64_t so = 0, sl = 0;
+        if (act) { call_span(g, j, start, n); so = in_off[j]; sl = in_off[j + 1] - so; }
+        uint8_t *op = out + start;
+        if (act && sl == n) { group_copy(op, in + so, n, i, 16); act = false; }              // raw chunk (CCPY turborc.c:434)
+        if (!act) n = 0;
+        const uint32_t n32 = (uint32_t)n, n_o = __shfl_xor_sync(FULLMASK, n32, 16), nmax = n32 > n_o ? n32 : n_o;
+        // ---- coders and their stream rings
+        Rc3 d[NC];
+        const uint8_t *stream = act ? in + so : gend;
+        d[0].sp = stream + (NC == 2 ? 4 : 0);
+        if (NC == 2) {
+            const uint32_t len0 = ld_u32_clamped(stream, gend);                                // rccdf.c:215
+            const uint8_t *p1 = stream + 4 + len0;
+            d[NC - 1].sp = (p1 > gend || p1 < stream) ? gend : p1;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            d[c].ring = rings + c * R3_RING;
+            d[c].ring[i] = ld32_any(d[c].sp + 4 * i, gend);
+            d[c].pend = ld32_any(d[c].sp + 64 + 4 * i, gend);
+            d[c].wf = 16; d[c].wp = 2;
+        }
+        for (uint32_t k = i; k < (uint32_t)O1_CTX_ENTRIES; k += 16) T[k] = (uint16_t)((k & 15) << 11);   // CDF16DEC0/1 (rccdf.c:188)
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < NC; c++) {                                                         // rcdinit turborc_.h:152-158
+            d[c].rl = d[c].rh = 0xffffffffu; d[c].ch = d[c].ring[0]; d[c].cl = d[c].ring[1];
+        }
+        auto refill = [&]() {
+            bool need = false;
+#pragma unroll
+            for (int c = 0; c < NC; c++) need = need || d[c].wf - d[c].wp <= 16;               // then the slots to overwrite have been consumed
+            if (__any_sync(FULLMASK, need)) {
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < NC; c++)
+                    if (d[c].wf - d[c].wp <= 16) {
+                        d[c].ring[(d[c].wf & (R3_RING - 1)) + i] = d[c].pend;
+                        d[c].wf += 16;
+                        d[c].pend = ld32_any(d[c].sp + 4 * (size_t)d[c].wf + 4 * i, gend);
+                    }
+                __syncwarp();
+            }
+        };
+        int mh = (int)(i << 11);                                                               // high-nibble table: stays in its register
+        for (uint32_t k = 0; k < nmax; k += 4) {                                               // four bytes per trip: <= 8 words per coder
+            refill();
+            uint32_t w = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {                                                      // cdf8d / cdf8d2 rccdf_.h:50-73
+                const uint32_t h = r3_nib(d[0], mh, i, hbm1, hm, c10, c10mix);
+                uint16_t *e = Ti + h * 16;
+                int m = *e;
+                const uint32_t l = r3_nib(d[NC - 1], m, i, hbm1, hm, c10, c10mix);
+                *e = (uint16_t)m;
+                w |= (h * 16 + l - 17) << (8 * b);
+            }
+            const uint32_t o = k + (lane & 3);
+            if (writer && o < n32) op[o] = (uint8_t)(w >> (8 * (lane & 3)));
+        }
+    }
+}
+
 }  // namespace trc

@@ -317,8 +317,10 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
         break;
     }
     case RC:    if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_dec<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g);
+                else if (g_adapt_v3) k_rc_dec3<1><<<blocks(g.n_calls, 2 * D3_WPB), D3_WPB * 32, r3_smem_bytes<1>(), st>>>(d_in, d_in_off, d_out, g);
                 else k_rc_byte_dec_coop<1><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, d_in_off, d_out, g); break;
     case RCI:   if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_dec<R_BYTE2, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g);
+                else if (g_adapt_v3) k_rc_dec3<2><<<blocks(g.n_calls, 2 * D3_WPB), D3_WPB * 32, r3_smem_bytes<2>(), st>>>(d_in, d_in_off, d_out, g);
                 else k_rc_byte_dec_coop<2><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, d_in_off, d_out, g); break;
     case RC4:   k_rc_adapt_dec<R_NIB1, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
     case RC4I:  k_rc_adapt_dec<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
