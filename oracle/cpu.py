@@ -38,6 +38,13 @@ DECODERS = {
     # port-only (no reference counterpart): true inverses with the tail state fixed / wide alphabet
     "ans_sdec_n": (True, True), "anscdf4dec_fix": (False, False), "answdec": (True, True),
 }
+# VLC-over-CDF integer codecs: (family, element bits); input/output are little-endian integers
+VLC_CODECS = [("anscdfu", 16), ("anscdfuz", 16), ("anscdfv", 16), ("anscdfvz", 16), ("anscdfv", 32), ("anscdfvz", 32),
+              ("rccdfv", 16), ("rccdfvz", 16), ("rccdfv", 32), ("rccdfvz", 32), ("rccdfu", 16), ("rccdfu", 32)]
+for _n, _w in VLC_CODECS:
+    ENCODERS[f"{_n}enc{_w}"] = (False, False)
+    DECODERS[f"{_n}dec{_w}"] = (False, False)
+
 PAIRS = {  # encoder -> decoder the reference harness pairs it with (turborc.c:495-536)
     "anscdf4senc": "anscdf4sdec", "anscdf4enc": "anscdf4dec", "anscdfenc": "anscdfdec",
     "anscdf1enc": "anscdf1dec", "rccdfsenc": "rccdfsbdec", "rccdfs2enc": "rccdfsb2dec",

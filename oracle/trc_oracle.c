@@ -545,6 +545,171 @@ size_t orc_rccdfidec8(const uint8_t *in, size_t outlen, uint8_t *out) {         
     return outlen;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * VLC-over-CDF integer codecs: anscdf{u,uz,v,vz}{enc,dec}16, anscdf{v,vz}{enc,dec}32
+ * (anscdf.c:139-483) and rccdf{v,vz,u}{enc,dec}{16,32} (rccdf.c:392-632).  Every 16/32-bit integer (optionally the zigzag
+ * of its delta to the previous one) goes through Turbo VLC (include_/vlcbit.h:24-63): values below 2^(vn+1) are their own
+ * symbol, larger ones become an exponent symbol (6 or 7 bits) plus mb mantissa bits written to a bit stream that grows
+ * DOWNWARD from the end of the output (bit IO rcutil_.h:163-192).  The symbol is coded with two adaptive 16-entry tables
+ * (cdfenc6 / cdfenc7 anscdf_.h:206-230, cdfe6 / cdfe7 rccdf_.h:100-122) by the 2-state blocked rANS or one range coder.
+ * Stream: [u32 total length][entropy-coded part][bit stream], the decoder starts its bit reader at in + u32.
+ * ------------------------------------------------------------------------------------------ */
+static uint64_t ld64(const uint8_t *p) { uint64_t v; memcpy(&v, p, 8); return v; }
+static void st64(uint8_t *p, uint64_t v) { memcpy(p, &v, 8); }
+typedef struct { uint64_t bw; unsigned br; uint8_t *p; } bitw;                 /* biteinir / bitput / bitenormr / bitflushr */
+static void bw_init(bitw *b, uint8_t *end) { b->bw = 0; b->br = 64; b->p = end - 8; }
+static void bw_put(bitw *b, unsigned nb, uint32_t x) { b->br -= nb; b->bw |= (uint64_t)x << b->br; }
+static void bw_norm(bitw *b) { st64(b->p, b->bw); unsigned k = (64 - b->br) & ~7u; b->p -= k >> 3; b->bw <<= k; b->br += k; }
+static void bw_flush(bitw *b) { st64(b->p, b->bw); unsigned k = (64 + 7 - b->br) & ~7u; b->p -= k >> 3; b->p += 8; }
+typedef struct { uint64_t bw; unsigned br; const uint8_t *p; } bitr;           /* bitdinir / bitdnormr / bitpeek / bitrmv */
+static void br_init(bitr *b, const uint8_t *end) { b->bw = 0; b->br = 0; b->p = end - 8; }
+static void br_norm(bitr *b) { b->p -= b->br >> 3; b->bw = ld64(b->p); b->br &= 7; }
+static unsigned bsr32(uint32_t x) { unsigned r = 0; while (x >>= 1) r++; return r; }
+/* bitvrput with vb = 0 (vlcbit.h:40-48): mantissa to the bit stream, returns the symbol to entropy-code */
+static unsigned vlc_put(bitw *b, unsigned vn, uint32_t x) {
+    if (x >= (1u << (vn + 1))) {
+        unsigned f = bsr32(x) - vn, expo = ((f + 1) << vn) + ((x >> f) & ((1u << vn) - 1)), mb = (expo >> vn) - 1;
+        bw_put(b, mb, x & ((1u << mb) - 1)); bw_norm(b);
+        x = expo;
+    }
+    return x;
+}
+static uint32_t vlc_get(bitr *b, unsigned vn, uint32_t x) {                    /* bitvrget vlcbit.h:59-64 */
+    if (x >= (1u << (vn + 1))) {
+        br_norm(b);
+        unsigned mb = (x >> vn) - 1;
+        uint32_t ma = (uint32_t)((b->bw << b->br) >> (64 - mb));
+        x = (((1u << vn) + (x & ((1u << vn) - 1))) << mb) + ma;
+        b->br += mb;
+    }
+    return x;
+}
+static uint32_t vlc_load(const uint8_t *in, size_t i, int w32) { if (w32) return ld32(in + 4 * i); return ld16(in + 2 * i); }
+static uint32_t zz_enc(uint32_t cur, uint32_t prev, int w32) {                  /* zigzagenc16/32 of the difference (rcutil_.h:144-148) */
+    if (w32) { int32_t d = (int32_t)(cur - prev); return ((uint32_t)d << 1) ^ (uint32_t)(d >> 31); }
+    int16_t d = (int16_t)(cur - prev); return (uint16_t)(((uint16_t)d << 1) ^ (uint16_t)(d >> 15));
+}
+static uint32_t zz_dec(uint32_t r, int w32) {
+    if (w32) return (r >> 1) ^ (0u - (r & 1));
+    uint16_t v = (uint16_t)r; return (uint16_t)((v >> 1) ^ (uint16_t)(0u - (v & 1)));
+}
+/* kind: vn = 1 -> 6-bit exponent, first symbol range 0..11 (cdfenc6); vn = 2 -> 7-bit exponent, 0..7 (cdfenc7) */
+static size_t vlc_ans_enc(const uint8_t *in, size_t inbytes, uint8_t *out, int w32, unsigned vn, int zz) {
+    const unsigned esz = w32 ? 4 : 2, lim = vn == 1 ? 12 : 8;
+    size_t n = (inbytes + esz - 1) / esz, blk = n < ANS_BLOCK ? n : ANS_BLOCK, pos = 0;
+    uint8_t *op = out + 4, *out_end = out + inbytes;
+    recstack s; s.base = (uint32_t *)malloc((blk * 2 + 16) * sizeof(uint32_t)); s.top = s.base;
+    bitw b; bw_init(&b, out_end);
+    uint32_t cx = 0;
+    while (pos < n) {
+        cdf_t m0[17], m1[17]; adapt_init(m0); adapt_init(m1);
+        size_t cnt = n - pos < blk ? n - pos : blk;
+        s.top = s.base;
+        for (size_t i = 0; i < cnt; i++) {
+            uint32_t v = vlc_load(in, pos + i, w32), x = zz ? zz_enc(v, cx, w32) : v;
+            cx = v;
+            x = vlc_put(&b, vn, x);
+            if (x < lim) model_push(&s, m0, 1, x);
+            else { x -= lim; model_push(&s, m0, 1, (x >> 4) + lim); model_push(&s, m1, 0, x & 15); }
+        }
+        if (block_flush(&s, 2, &op, b.p - 8)) goto raw;                        /* mnflush(op, bp-8, ...) */
+        pos += cnt;
+    }
+    bw_flush(&b);
+    {
+        size_t l = (size_t)(out_end - b.p);
+        if (op + l >= out_end) goto raw;
+        memmove(op, b.p, l); op += l;
+        st32(out, (uint32_t)(op - out));
+    }
+    free(s.base);
+    return (size_t)(op - out);
+raw:
+    memcpy(out, in, inbytes); free(s.base);
+    return inbytes;
+}
+static size_t vlc_ans_dec(const uint8_t *in, size_t outbytes, uint8_t *out, int w32, unsigned vn, int zz) {
+    const unsigned esz = w32 ? 4 : 2, lim = vn == 1 ? 12 : 8;
+    size_t n = (outbytes + esz - 1) / esz, blk = n < ANS_BLOCK ? n : ANS_BLOCK, pos = 0;
+    const uint8_t *ip = in + 4;
+    bitr b; br_init(&b, in + ld32(in));
+    uint32_t cx = 0;
+    while (pos < n) {
+        cdf_t m0[17], m1[17]; adapt_init(m0); adapt_init(m1);
+        uint32_t st[2];
+        size_t cnt = n - pos < blk ? n - pos : blk;
+        st[0] = ld32(ip); ip += 4; st[1] = ld32(ip); ip += 4;                   /* mnfill(st, ip, 2) */
+        for (size_t i = 0; i < cnt; i++) {
+#define VDEC(_s_, _m_, _x_) do { _x_ = rans_find16(_m_, st[_s_] & (PROB_TOTAL - 1)); st[_s_] = rans_get(st[_s_], _m_[_x_], _m_[_x_ + 1]); \
+                                 adapt_update(_m_, _x_); st[_s_] = rans_refill(st[_s_], &ip); } while (0)
+            unsigned x, y;
+            VDEC(0, m0, x);
+            if (x >= lim) { VDEC(1, m1, y); x = ((x - lim) << 4 | y) + lim; }
+#undef VDEC
+            uint32_t r = vlc_get(&b, vn, x);
+            if (zz) { cx += zz_dec(r, w32); r = cx; }
+            if (w32) st32(out + 4 * (pos + i), r); else st16(out + 2 * (pos + i), (uint16_t)r);
+        }
+        pos += cnt;
+    }
+    return outbytes;
+}
+static size_t vlc_rc_enc(const uint8_t *in, size_t inbytes, uint8_t *out, int w32, unsigned vn, int zz) {
+    const unsigned esz = w32 ? 4 : 2, lim = vn == 1 ? 12 : 8;
+    size_t n = (inbytes + esz - 1) / esz;
+    uint8_t *out_end = out + inbytes;
+    cdf_t m0[17], m1[17]; adapt_init(m0); adapt_init(m1);
+    rcenc e; rce_init(&e, out + 4);
+    bitw b; bw_init(&b, out_end);
+    uint32_t cx = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint32_t v = vlc_load(in, i, w32), x = zz ? zz_enc(v, cx, w32) : v;
+        x = vlc_put(&b, vn, x);
+        if (x < lim) rce_nib(&e, m0, x);
+        else { x -= lim; rce_nib(&e, m0, (x >> 4) + lim); rce_nib(&e, m1, x & 15); }
+        if (e.op + 8 >= b.p) { memcpy(out, in, inbytes); return inbytes; }      /* rccdf.c:406 */
+        cx = v;
+    }
+    rce_flush(&e);
+    bw_flush(&b);
+    size_t l = (size_t)(out_end - b.p);
+    memmove(e.op, b.p, l); e.op += l;
+    st32(out, (uint32_t)(e.op - out));
+    if (rc_overflow(e.op, out, inbytes)) { memcpy(out, in, inbytes); return inbytes; }
+    return (size_t)(e.op - out);
+}
+static size_t vlc_rc_dec(const uint8_t *in, size_t outbytes, uint8_t *out, int w32, unsigned vn, int zz) {
+    const unsigned esz = w32 ? 4 : 2, lim = vn == 1 ? 12 : 8;
+    size_t n = (outbytes + esz - 1) / esz;
+    cdf_t m0[17], m1[17]; adapt_init(m0); adapt_init(m1);
+    rcdec d; rcd_init(&d, in + 4);
+    bitr b; br_init(&b, in + ld32(in));
+    uint32_t cx = 0;
+    for (size_t i = 0; i < n; i++) {
+        unsigned x = rcd_nib(&d, m0);
+        if (x >= lim) { unsigned y = rcd_nib(&d, m1); x = ((x - lim) << 4 | y) + lim; }
+        uint32_t r = vlc_get(&b, vn, x);
+        if (zz) { cx += zz_dec(r, w32); r = cx; }
+        if (w32) st32(out + 4 * i, r); else st16(out + 2 * i, (uint16_t)r);
+    }
+    return outbytes;
+}
+#define VLC_PAIR(_name_, _fn_, _w32_, _vn_, _zz_) \
+    size_t orc_##_name_##enc##_w32_(const uint8_t *in, size_t n, uint8_t *out) { return _fn_##_enc(in, n, out, _w32_ == 32, _vn_, _zz_); } \
+    size_t orc_##_name_##dec##_w32_(const uint8_t *in, size_t n, uint8_t *out) { return _fn_##_dec(in, n, out, _w32_ == 32, _vn_, _zz_); }
+VLC_PAIR(anscdfu,  vlc_ans, 16, 1, 0)   /* anscdf.c:139-193 */
+VLC_PAIR(anscdfuz, vlc_ans, 16, 1, 1)   /* anscdf.c:195-252 */
+VLC_PAIR(anscdfv,  vlc_ans, 16, 2, 0)   /* anscdf.c:255-309 */
+VLC_PAIR(anscdfvz, vlc_ans, 16, 2, 1)   /* anscdf.c:311-367 */
+VLC_PAIR(anscdfv,  vlc_ans, 32, 2, 0)   /* anscdf.c:369-423 */
+VLC_PAIR(anscdfvz, vlc_ans, 32, 2, 1)   /* anscdf.c:425-483 */
+VLC_PAIR(rccdfv,   vlc_rc,  16, 2, 0)   /* rccdf.c:392-429 */
+VLC_PAIR(rccdfvz,  vlc_rc,  16, 2, 1)   /* rccdf.c:432-470 */
+VLC_PAIR(rccdfv,   vlc_rc,  32, 2, 0)   /* rccdf.c:473-512 */
+VLC_PAIR(rccdfvz,  vlc_rc,  32, 2, 1)   /* rccdf.c:515-553 */
+VLC_PAIR(rccdfu,   vlc_rc,  16, 1, 0)   /* rccdf.c:555-592 */
+VLC_PAIR(rccdfu,   vlc_rc,  32, 1, 0)   /* rccdf.c:595-632 */
+
 /* R11: nibble-alphabet adaptive RC (rccdf.c:251-323) */
 size_t orc_rccdf4enc(const uint8_t *in, size_t inlen, uint8_t *out) {
     cdf_t t[17]; adapt_init(t);
