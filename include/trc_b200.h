@@ -46,7 +46,11 @@ enum trc_codec {
                        the specification.  Static table like TRC_ANS4S; chunk_len must be a multiple of 4. */
     TRC_RC8   = 11, /* [f.3]   rccdfenc8   / rccdfdec8    adaptive RC over the vnibble byte code   rccdf.c:324-351  */
     TRC_RCI8  = 12, /* [f.3]   rccdfienc8  / rccdfidec8   same, 2 coders                           rccdf.c:354-389  */
-    TRC_NCODECS = 13
+    /* [f.2] VLC-over-CDF integer codecs: total_len / chunk_len are BYTES of little-endian 16- or 32-bit integers and must be
+       multiples of the element size.  u = 6-bit exponent, v = 7-bit exponent, z = zigzag delta.              anscdf.c:139-483 */
+    TRC_ANSU16 = 13, TRC_ANSUZ16 = 14, TRC_ANSV16 = 15, TRC_ANSVZ16 = 16, TRC_ANSV32 = 17, TRC_ANSVZ32 = 18,
+    TRC_RCV16 = 19, TRC_RCVZ16 = 20, TRC_RCV32 = 21, TRC_RCVZ32 = 22, TRC_RCU16 = 23, TRC_RCU32 = 24,          /* rccdf.c:392-632 */
+    TRC_NCODECS = 25
 };
 
 #define TRC_CDF_STRIDE 257                    /* entries per static table (cdf_t cdf[0x100+1], turborc.c:423) */
@@ -194,6 +198,19 @@ size_t rccdfenc8  (unsigned char *in, size_t inlen,  unsigned char *out);       
 size_t rccdfdec8  (unsigned char *in, size_t outlen, unsigned char *out);                                  /* rccdf.c:324 */
 size_t rccdfienc8 (unsigned char *in, size_t inlen,  unsigned char *out);                                  /* rccdf.c:371 */
 size_t rccdfidec8 (unsigned char *in, size_t outlen, unsigned char *out);                                  /* rccdf.c:354 */
+/* VLC-over-CDF integer codecs: lengths in bytes (multiples of the element size) */
+size_t anscdfuenc16 (unsigned char *in, size_t inlen, unsigned char *out);  size_t anscdfudec16 (unsigned char *in, size_t outlen, unsigned char *out);   /* anscdf.c:139,168 */
+size_t anscdfuzenc16(unsigned char *in, size_t inlen, unsigned char *out);  size_t anscdfuzdec16(unsigned char *in, size_t outlen, unsigned char *out);   /* anscdf.c:195,226 */
+size_t anscdfvenc16 (unsigned char *in, size_t inlen, unsigned char *out);  size_t anscdfvdec16 (unsigned char *in, size_t outlen, unsigned char *out);   /* anscdf.c:255,284 */
+size_t anscdfvzenc16(unsigned char *in, size_t inlen, unsigned char *out);  size_t anscdfvzdec16(unsigned char *in, size_t outlen, unsigned char *out);   /* anscdf.c:311,342 */
+size_t anscdfvenc32 (unsigned char *in, size_t inlen, unsigned char *out);  size_t anscdfvdec32 (unsigned char *in, size_t outlen, unsigned char *out);   /* anscdf.c:369,398 */
+size_t anscdfvzenc32(unsigned char *in, size_t inlen, unsigned char *out);  size_t anscdfvzdec32(unsigned char *in, size_t outlen, unsigned char *out);   /* anscdf.c:425,456 */
+size_t rccdfvenc16  (unsigned char *in, size_t inlen, unsigned char *out);  size_t rccdfvdec16  (unsigned char *in, size_t outlen, unsigned char *out);   /* rccdf.c:392,413 */
+size_t rccdfvzenc16 (unsigned char *in, size_t inlen, unsigned char *out);  size_t rccdfvzdec16 (unsigned char *in, size_t outlen, unsigned char *out);   /* rccdf.c:432,454 */
+size_t rccdfvenc32  (unsigned char *in, size_t inlen, unsigned char *out);  size_t rccdfvdec32  (unsigned char *in, size_t outlen, unsigned char *out);   /* rccdf.c:473,495 */
+size_t rccdfvzenc32 (unsigned char *in, size_t inlen, unsigned char *out);  size_t rccdfvzdec32 (unsigned char *in, size_t outlen, unsigned char *out);   /* rccdf.c:515,537 */
+size_t rccdfuenc16  (unsigned char *in, size_t inlen, unsigned char *out);  size_t rccdfudec16  (unsigned char *in, size_t outlen, unsigned char *out);   /* rccdf.c:555,576 */
+size_t rccdfuenc32  (unsigned char *in, size_t inlen, unsigned char *out);  size_t rccdfudec32  (unsigned char *in, size_t outlen, unsigned char *out);   /* rccdf.c:595,616 */
 
 #ifdef __cplusplus
 }

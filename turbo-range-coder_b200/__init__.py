@@ -18,13 +18,19 @@ LIB_PATH = os.path.join(_HERE, "libtrc_b200.so")
 
 # enum trc_codec (include/trc_b200.h)
 ANS4S, ANS4, ANS, ANS1, RCS, RCS2, RC, RCI, RC4, RC4I, ANSW, RC8, RCI8 = range(13)
-CODEC_NAMES = ["ANS4S", "ANS4", "ANS", "ANS1", "RCS", "RCS2", "RC", "RCI", "RC4", "RC4I", "ANSW", "RC8", "RCI8"]
+(ANSU16, ANSUZ16, ANSV16, ANSVZ16, ANSV32, ANSVZ32, RCV16, RCVZ16, RCV32, RCVZ32, RCU16, RCU32) = range(13, 25)   # VLC-over-CDF integer codecs
+CODEC_NAMES = ["ANS4S", "ANS4", "ANS", "ANS1", "RCS", "RCS2", "RC", "RCI", "RC4", "RC4I", "ANSW", "RC8", "RCI8",
+               "ANSU16", "ANSUZ16", "ANSV16", "ANSVZ16", "ANSV32", "ANSVZ32", "RCV16", "RCVZ16", "RCV32", "RCVZ32", "RCU16", "RCU32"]
 #: codec id -> (reference encoder, reference decoder)
 REF_NAMES = {
     ANS4S: ("anscdf4senc", "anscdf4sdec"), ANS4: ("anscdf4enc", "anscdf4dec"), ANS: ("anscdfenc", "anscdfdec"),
     ANS1: ("anscdf1enc", "anscdf1dec"), RCS: ("rccdfsenc", "rccdfsbdec"), RCS2: ("rccdfs2enc", "rccdfsb2dec"),
     RC: ("rccdfenc", "rccdfdec"), RCI: ("rccdfienc", "rccdfidec"), RC4: ("rccdf4enc", "rccdf4dec"),
     RC4I: ("rccdf4ienc", "rccdf4idec"), RC8: ("rccdfenc8", "rccdfdec8"), RCI8: ("rccdfienc8", "rccdfidec8"),
+    ANSU16: ("anscdfuenc16", "anscdfudec16"), ANSUZ16: ("anscdfuzenc16", "anscdfuzdec16"), ANSV16: ("anscdfvenc16", "anscdfvdec16"),
+    ANSVZ16: ("anscdfvzenc16", "anscdfvzdec16"), ANSV32: ("anscdfvenc32", "anscdfvdec32"), ANSVZ32: ("anscdfvzenc32", "anscdfvzdec32"),
+    RCV16: ("rccdfvenc16", "rccdfvdec16"), RCVZ16: ("rccdfvzenc16", "rccdfvzdec16"), RCV32: ("rccdfvenc32", "rccdfvdec32"),
+    RCVZ32: ("rccdfvzenc32", "rccdfvzdec32"), RCU16: ("rccdfuenc16", "rccdfudec16"), RCU32: ("rccdfuenc32", "rccdfudec32"),
 }
 STATIC = (ANS4S, RCS, RCS2, ANSW)
 F_REF_TAIL = 1
@@ -256,6 +262,8 @@ _ENC3 = ["anscdf4enc", "anscdfenc", "anscdf1enc", "rccdfenc", "rccdfienc", "rccd
          "anscdf4encs", "anscdf4encx", "anscdfencs", "anscdfencx", "anscdf1encs", "anscdf1encx"]
 _DEC3 = ["anscdf4dec", "anscdfdec", "anscdf1dec", "rccdfdec", "rccdfidec", "rccdf4dec", "rccdf4idec", "rccdfdec8", "rccdfidec8",
          "anscdf4decs", "anscdf4decx", "anscdfdecs", "anscdfdecx", "anscdf1decs", "anscdf1decx"]
+_ENC3 += [e for c, (e, d) in sorted(REF_NAMES.items()) if c >= ANSU16]
+_DEC3 += [d for c, (e, d) in sorted(REF_NAMES.items()) if c >= ANSU16]
 _ENC4 = ["anscdf4senc", "anscdf4sencs", "anscdf4sencx"]
 _DEC4 = ["anscdf4sdec", "anscdf4sdecs", "anscdf4sdecx"]
 _ENC5 = ["rccdfsenc", "rccdfs2enc"]

@@ -9,6 +9,7 @@
 #include "adaptive_coop.cuh"
 #include "adaptive_v3.cuh"
 #include "vnibble.cuh"
+#include "vlc.cuh"
 #include "rans_wide.cuh"
 #include "pack.cuh"
 #include <cstdio>
@@ -82,8 +83,18 @@ static int make_plan(int codec, size_t total_len, size_t chunk_len, Plan &p) {
     p.g = make_geom(codec, total_len, chunk_len);
     const bool blocked = codec_blocked(codec);
     p.slot_stride = (blocked && p.g.upc > 1) ? al16(4 * (size_t)p.g.unit_max + 64) : al16(p.g.unit_max) + (codec == ANSW ? 448 : 192);
+    if (codec_vlc(codec)) {                                      // integer codecs: whole elements per call
+        const size_t esz = vlc_param(codec).w32 ? 4 : 2;
+        if (total_len % esz || (chunk_len < total_len && chunk_len % esz)) return TRC_E_ARG;
+        if (codec_vlc_ans(codec)) p.slot_stride = vlc_lifo_off(p.g.unit_max) + al16(p.g.unit_max) + 192;   // out image + aligned LIFO scratch
+    }
     if (codec == ANSW && (chunk_len & 3)) return TRC_E_ARG;                                   // our own format: calls start 4-byte aligned
     p.rec_stride = blocked ? (((size_t)2 * p.g.unit_max + 3) & ~(size_t)3) + 16 : 0;
+    if (codec_vlc_ans(codec)) {                                  // at most two records per element, one block (4 Mi elements) at a time
+        size_t el = p.g.unit_max / (vlc_param(codec).w32 ? 4 : 2) + 1;
+        if (el > ANS_BLOCK) el = ANS_BLOCK;
+        p.rec_stride = ((2 * el + 3) & ~(size_t)3) + 16;
+    }
     p.o1_threads = 0;
     // (order-1 tables live in shared memory since the warp-cooperative kernels; no global table scratch)
     size_t o = 0;
@@ -238,6 +249,10 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     case RC4I:  k_rc_adapt_enc<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
     case RC8:   k_rc_v8_enc<1><<<blocks(g.n_calls, V8_NT), V8_NT, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
     case RCI8:  k_rc_v8_enc<2><<<blocks(g.n_calls, V8_NT), V8_NT, 0, st>>>(d_in, g, slots, p.slot_stride, meta); break;
+    default:
+        if (codec_vlc_ans(codec)) k_vlc_ans_enc<<<blocks(g.n_calls, VLC_NT), VLC_NT, 0, st>>>(d_in, g, vlc_param(codec), slots, p.slot_stride, recs, p.rec_stride, meta);
+        else if (codec_vlc(codec)) k_vlc_rc_enc<<<blocks(g.n_calls, VLC_NT), VLC_NT, 0, st>>>(d_in, g, vlc_param(codec), slots, p.slot_stride, meta);
+        break;
     }
     CK_LAUNCH(); prof_mark(st);
     k_resolve<<<blocks(g.n_calls, 256), 256, 0, st>>>(g, codec_blocked(codec) ? 1 : 0, meta, calls);
@@ -326,6 +341,10 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
     case RC4I:  k_rc_adapt_dec<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
     case RC8:   k_rc_v8_dec<1><<<blocks(g.n_calls, V8_NT), V8_NT, 0, st>>>(d_in, d_in_off, d_out, g); break;
     case RCI8:  k_rc_v8_dec<2><<<blocks(g.n_calls, V8_NT), V8_NT, 0, st>>>(d_in, d_in_off, d_out, g); break;
+    default:
+        if (codec_vlc_ans(codec)) k_vlc_dec<false><<<blocks(g.n_calls, VLC_NT), VLC_NT, 0, st>>>(d_in, d_in_off, d_out, g, vlc_param(codec));
+        else if (codec_vlc(codec)) k_vlc_dec<true><<<blocks(g.n_calls, VLC_NT), VLC_NT, 0, st>>>(d_in, d_in_off, d_out, g, vlc_param(codec));
+        break;
     }
     CK_LAUNCH(); prof_mark(st);
     return TRC_OK;
@@ -802,6 +821,13 @@ ENC3(rccdf4enc, RC4) DEC3(rccdf4dec, RC4, 0)
 ENC3(rccdf4ienc, RC4I) DEC3(rccdf4idec, RC4I, 0)
 ENC3(rccdfenc8, RC8) DEC3(rccdfdec8, RC8, 0)
 ENC3(rccdfienc8, RCI8) DEC3(rccdfidec8, RCI8, 0)
+// VLC-over-CDF integer codecs (anscdf.c:139-483, rccdf.c:392-632): inlen / outlen are BYTES of 16/32-bit little-endian integers
+ENC3(anscdfuenc16, ANSU16) DEC3(anscdfudec16, ANSU16, 0) ENC3(anscdfuzenc16, ANSUZ16) DEC3(anscdfuzdec16, ANSUZ16, 0)
+ENC3(anscdfvenc16, ANSV16) DEC3(anscdfvdec16, ANSV16, 0) ENC3(anscdfvzenc16, ANSVZ16) DEC3(anscdfvzdec16, ANSVZ16, 0)
+ENC3(anscdfvenc32, ANSV32) DEC3(anscdfvdec32, ANSV32, 0) ENC3(anscdfvzenc32, ANSVZ32) DEC3(anscdfvzdec32, ANSVZ32, 0)
+ENC3(rccdfvenc16, RCV16) DEC3(rccdfvdec16, RCV16, 0) ENC3(rccdfvzenc16, RCVZ16) DEC3(rccdfvzdec16, RCVZ16, 0)
+ENC3(rccdfvenc32, RCV32) DEC3(rccdfvdec32, RCV32, 0) ENC3(rccdfvzenc32, RCVZ32) DEC3(rccdfvzdec32, RCVZ32, 0)
+ENC3(rccdfuenc16, RCU16) DEC3(rccdfudec16, RCU16, 0) ENC3(rccdfuenc32, RCU32) DEC3(rccdfudec32, RCU32, 0)
 
 #define ENC5(name, codec) size_t name(unsigned char *in, size_t inlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum) { return dropin_enc(#name, codec, in, inlen, out, cdf, cdfnum); }
 #define DEC5(name, codec) size_t name(unsigned char *in, size_t outlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum) { return dropin_dec(#name, codec, in, outlen, out, cdf, cdfnum, 0); }

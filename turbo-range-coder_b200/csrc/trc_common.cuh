@@ -23,7 +23,9 @@ constexpr uint32_t ANS_L      = 1u << 15;          // ANS_LOW anscdf_.h:40-41
 constexpr uint32_t ANS_BLOCK  = 1u << 22;          // ANSBLKSIZE anscdf.c:54
 constexpr int      CDF_STRIDE = 257;
 
-enum Codec { ANS4S = 0, ANS4, ANS, ANS1, RCS, RCS2, RC, RCI, RC4, RC4I, ANSW, RC8, RCI8, NCODECS };
+enum Codec { ANS4S = 0, ANS4, ANS, ANS1, RCS, RCS2, RC, RCI, RC4, RC4I, ANSW, RC8, RCI8,
+             ANSU16, ANSUZ16, ANSV16, ANSVZ16, ANSV32, ANSVZ32, RCV16, RCVZ16, RCV32, RCVZ32, RCU16, RCU32,   // VLC-over-CDF integer codecs (vlc.cuh)
+             NCODECS };
 
 __host__ __device__ inline bool codec_blocked(int c) { return c == ANS4 || c == ANS || c == ANS1; }
 __host__ __device__ inline bool codec_static(int c)  { return c == ANS4S || c == RCS || c == RCS2 || c == ANSW; }
