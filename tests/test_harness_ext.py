@@ -42,7 +42,7 @@ def test_harness_cpu_ids_run(tmp_path, dg):
         pytest.skip("oracle/_ref/turborc_gpu not built")
     src = tmp_path / "z.bin"
     dg.zipf(200_000).tofile(src)
-    r = subprocess.run([BIN, "-e45,56", str(src)], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([BIN, "-I1", "-J1", "-e45,56", str(src)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ERROR" not in r.stdout.upper(), r.stdout + r.stderr
     rows = _rows(r.stdout)
     assert set(rows) == {45, 56}, r.stdout
@@ -58,7 +58,7 @@ def test_harness_gpu_rows(tmp_path, dg, port):
     for name, (data, ids) in cases.items():
         src = tmp_path / f"{name}.bin"
         data.tofile(src)
-        r = subprocess.run([BIN, "-e" + ids, str(src)], capture_output=True, text=True, timeout=900)
+        r = subprocess.run([BIN, "-I1", "-J1", "-e" + ids, str(src)], capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stdout + r.stderr
         assert "ERROR" not in (r.stdout + r.stderr).upper(), r.stdout + r.stderr    # memcheck(in, n, cpy) after every id
         rows = _rows(r.stdout)

@@ -207,7 +207,6 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     CallInfo *calls = (CallInfo *)(sc + p.off_calls);
     uint8_t *slots = sc + p.off_slots;
     uint32_t *recs = (uint32_t *)(sc + p.off_recs);
-    uint32_t *o1 = (uint32_t *)(sc + p.off_o1);
     const Geom &g = p.g;
     auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
     g_prof_n = 0;
@@ -239,7 +238,7 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
         static bool attr = false;
         if (!attr) { CK(cudaFuncSetAttribute(k_ans_byte_enc_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)O1_SMEM_BYTES)); attr = true; }
         k_ans_byte_enc_coop<true><<<(unsigned)(g.n_units < 148 ? g.n_units : 148), 32, O1_SMEM_BYTES, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta);
-        (void)o1; break;
+        break;
     }
     case RC:    if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_enc<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, meta);
                 else k_rc_byte_enc_coop<1><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, g, slots, p.slot_stride, meta, g_force_redo); break;
