@@ -16,6 +16,7 @@ typedef unsigned short cdf_t;
 int    cdfini(unsigned char *in, size_t inlen, cdf_t *cdf, unsigned cdfnum);
 size_t rccdfsenc(unsigned char *, size_t, unsigned char *, cdf_t *, unsigned), rccdfsbdec(unsigned char *, size_t, unsigned char *, cdf_t *, unsigned);
 size_t rccdfsldec(unsigned char *, size_t, unsigned char *, cdf_t *, unsigned);
+size_t rccdfsvbdec(unsigned char *, size_t, unsigned char *, cdf_t *, unsigned), rccdfsvldec(unsigned char *, size_t, unsigned char *, cdf_t *, unsigned);
 size_t rccdfs2enc(unsigned char *, size_t, unsigned char *, cdf_t *, unsigned), rccdfsb2dec(unsigned char *, size_t, unsigned char *, cdf_t *, unsigned);
 size_t rccdfsl2dec(unsigned char *, size_t, unsigned char *, cdf_t *, unsigned);
 size_t rccdfenc(unsigned char *, size_t, unsigned char *), rccdfdec(unsigned char *, size_t, unsigned char *);
@@ -49,6 +50,7 @@ int main(int argc, char **argv) {
 #define CCPY(dec) (l == n ? (size_t)memcpy(cpy, out, n) : (dec))
     switch (id) {
     case 42: l = rccdfsenc(in, n, out, cdf, m + 1);  CCPY(m < 16 ? rccdfsldec(out, n, cpy, cdf, m + 1) : rccdfsbdec(out, n, cpy, cdf, m + 1)); break;
+    case 43: l = rccdfsenc(in, n, out, cdf, m + 1);  CCPY(m < 16 ? rccdfsvldec(out, n, cpy, cdf, m + 1) : rccdfsvbdec(out, n, cpy, cdf, m + 1)); break;   /* turborc.c:496 */
     case 45: l = rccdfs2enc(in, n, out, cdf, m + 1); CCPY(m < 16 ? rccdfsl2dec(out, n, cpy, cdf, m + 1) : rccdfsb2dec(out, n, cpy, cdf, m + 1)); break;
     case 46: if (m < 16) { l = rccdf4enc(in, n, out); CCPY(rccdf4dec(out, n, cpy)); } else { l = rccdfenc(in, n, out); CCPY(rccdfdec(out, n, cpy)); } break;
     case 47: if (m < 16) { l = rccdf4ienc(in, n, out); CCPY(rccdf4idec(out, n, cpy)); } else { l = rccdfienc(in, n, out); CCPY(rccdfidec(out, n, cpy)); } break;

@@ -183,6 +183,8 @@ int    cdfini(unsigned char *in, size_t inlen, cdf_t *cdf, unsigned cdfnum);    
 size_t rccdfsenc  (unsigned char *in, size_t inlen,  unsigned char *out, cdf_t *cdf, unsigned cdfnum);     /* rccdf.c:71  */
 size_t rccdfsbdec (unsigned char *in, size_t outlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum);     /* rccdf.c:92  */
 size_t rccdfsldec (unsigned char *in, size_t outlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum);     /* rccdf.c:84  */
+size_t rccdfsvbdec(unsigned char *in, size_t outlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum);     /* rccdf.c:100 (same stream, search by division: same symbols) */
+size_t rccdfsvldec(unsigned char *in, size_t outlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum);     /* rccdf.c:112 */
 size_t rccdfs2enc (unsigned char *in, size_t inlen,  unsigned char *out, cdf_t *cdf, unsigned cdfnum);     /* rccdf.c:125 */
 size_t rccdfsb2dec(unsigned char *in, size_t outlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum);     /* rccdf.c:166 */
 size_t rccdfsl2dec(unsigned char *in, size_t outlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum);     /* rccdf.c:146 */

@@ -24,7 +24,7 @@ def test_demo_binaries_link():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("ident", [42, 45, 46, 47, 48, 49, 56, 64, 65])
+@pytest.mark.parametrize("ident", [42, 43, 45, 46, 47, 48, 49, 56, 64, 65])
 def test_same_source_same_bytes(tmp_path, ident):
     if not os.path.exists(REF_BIN):
         pytest.skip("host/_build/dropin_demo_ref not built (needs oracle/_ref)")

@@ -267,7 +267,7 @@ _DEC3 += [d for c, (e, d) in sorted(REF_NAMES.items()) if c >= ANSU16]
 _ENC4 = ["anscdf4senc", "anscdf4sencs", "anscdf4sencx"]
 _DEC4 = ["anscdf4sdec", "anscdf4sdecs", "anscdf4sdecx"]
 _ENC5 = ["rccdfsenc", "rccdfs2enc"]
-_DEC5 = ["rccdfsbdec", "rccdfsldec", "rccdfsb2dec", "rccdfsl2dec"]
+_DEC5 = ["rccdfsbdec", "rccdfsldec", "rccdfsb2dec", "rccdfsl2dec", "rccdfsvbdec", "rccdfsvldec"]
 DROPIN_SYMBOLS = _ENC3 + _DEC3 + _ENC4 + _DEC4 + _ENC5 + _DEC5 + ["cdfini", "anscdfini"]
 
 

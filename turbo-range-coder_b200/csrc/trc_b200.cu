@@ -832,6 +832,7 @@ ENC3(rccdfuenc16, RCU16) DEC3(rccdfudec16, RCU16, 0) ENC3(rccdfuenc32, RCU32) DE
 #define DEC5(name, codec) size_t name(unsigned char *in, size_t outlen, unsigned char *out, cdf_t *cdf, unsigned cdfnum) { return dropin_dec(#name, codec, in, outlen, out, cdf, cdfnum, 0); }
 ENC5(rccdfsenc, RCS) DEC5(rccdfsbdec, RCS) DEC5(rccdfsldec, RCS)          // linear and binary search find the same symbol
 ENC5(rccdfs2enc, RCS2) DEC5(rccdfsb2dec, RCS2) DEC5(rccdfsl2dec, RCS2)
+DEC5(rccdfsvbdec, RCS) DEC5(rccdfsvldec, RCS)     // harness id 43: the same stream decoded by division, floor(code / range) >= cdf[x]  <=>  cdf[x] * range <= code (rccdf.c:100-122)
 
 int cdfini(unsigned char *in, size_t inlen, cdf_t *cdf, unsigned cdfnum) {
     if (inlen == 0 || cdfnum == 0 || cdfnum > 256) { fprintf(stderr, "Fatal cdf: empty input\n"); exit(-1); }
