@@ -34,12 +34,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CODECS = {"ans4s": 0, "ans4": 1, "ans": 2, "ans1": 3, "rcs": 4, "rcs2": 5, "rc": 6, "rci": 7, "rc4": 8, "rc4i": 9, "answ": 10, "rc8": 11, "rci8": 12}
+CODECS = {"ans4s": 0, "ans4": 1, "ans": 2, "ans1": 3, "rcs": 4, "rcs2": 5, "rc": 6, "rci": 7, "rc4": 8, "rc4i": 9, "answ": 10, "rc8": 11, "rci8": 12,
+          "ansu16": 13, "ansuz16": 14, "ansv16": 15, "ansvz16": 16, "ansv32": 17, "ansvz32": 18, "rcv16": 19, "rcvz16": 20, "rcv32": 21, "rcvz32": 22, "rcu16": 23, "rcu32": 24}
 REF_FN = {0: ("anscdf4senc", "anscdf4sdec"), 1: ("anscdf4enc", "anscdf4dec"), 2: ("anscdfenc", "anscdfdec"),
           3: ("anscdf1enc", "anscdf1dec"), 4: ("rccdfsenc", "rccdfsbdec"), 5: ("rccdfs2enc", "rccdfsb2dec"),
           6: ("rccdfenc", "rccdfdec"), 7: ("rccdfienc", "rccdfidec"), 8: ("rccdf4enc", "rccdf4dec"),
           9: ("rccdf4ienc", "rccdf4idec"),
           11: ("rccdfenc8", "rccdfdec8"), 12: ("rccdfienc8", "rccdfidec8"),
+          13: ("anscdfuenc16", "anscdfudec16"), 14: ("anscdfuzenc16", "anscdfuzdec16"), 15: ("anscdfvenc16", "anscdfvdec16"),
+          16: ("anscdfvzenc16", "anscdfvzdec16"), 17: ("anscdfvenc32", "anscdfvdec32"), 18: ("anscdfvzenc32", "anscdfvzdec32"),
+          19: ("rccdfvenc16", "rccdfvdec16"), 20: ("rccdfvzenc16", "rccdfvzdec16"), 21: ("rccdfvenc32", "rccdfvdec32"),
+          22: ("rccdfvzenc32", "rccdfvzdec32"), 23: ("rccdfuenc16", "rccdfudec16"), 24: ("rccdfuenc32", "rccdfudec32"),
           10: ("answenc", "answdec")}       # this repository's 32-way interleaved static rANS: no reference function, CPU leg = oracle port
 METRIC = "encode+decode GB/s on 100MB order-0 byte stream; bitstream bit-exact vs ref"
 SRC_NAME = {"zipf": "Zipf(1.1)", "bwt": "BWT-shaped", "o1": "order-1 Markov", "uniform": "uniform random"}

@@ -8,7 +8,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 trc = importlib.import_module("turbo-range-coder_b200")
 dg = importlib.import_module("turbo-range-coder_b200.datagen")
-CODECS = {"ans4s": 0, "ans4": 1, "ans": 2, "ans1": 3, "rcs": 4, "rcs2": 5, "rc": 6, "rci": 7, "rc4": 8, "rc4i": 9, "answ": 10, "rc8": 11, "rci8": 12}
+CODECS = {"ans4s": 0, "ans4": 1, "ans": 2, "ans1": 3, "rcs": 4, "rcs2": 5, "rc": 6, "rci": 7, "rc4": 8, "rc4i": 9, "answ": 10, "rc8": 11, "rci8": 12,
+          "ansu16": 13, "ansuz16": 14, "ansv16": 15, "ansvz16": 16, "ansv32": 17, "ansvz32": 18, "rcv16": 19, "rcvz16": 20, "rcv32": 21, "rcvz32": 22, "rcu16": 23, "rcu32": 24}
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=100_000_000)
