@@ -384,7 +384,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--codec", default="rcs2", choices=sorted(CODECS))
-    ap.add_argument("--chunk", type=int, default=4096)
+    ap.add_argument("--chunk", type=int, default=2048, help="bytes per reference call (2 KiB: twice the coder chains of 4 KiB, +0.2 %% compressed size; DESIGN.md section 5)")
     ap.add_argument("--size", type=int, default=100_000_000)
     ap.add_argument("--bytes-alphabet", action="store_true", help="ans4s: code full bytes with a 256-entry table")
     ap.add_argument("--src", default="zipf", choices=["zipf", "bwt", "o1", "uniform"], help="synthetic source (SURVEY.md section 8d)")

@@ -24,6 +24,7 @@ using namespace trc;
 static thread_local char g_err[256] = "";
 static int g_dev = 0;
 static const int g_force_redo = getenv("TRC_FORCE_REDO") ? 1 : 0;   // test hook: exercise the rare walk-back redo paths
+static const int g_fused = getenv("TRC_FUSED") ? atoi(getenv("TRC_FUSED")) : 1;             // 0: coder, scan and pack as separate kernels (A/B runs)
 static const int g_adapt_v3 = getenv("TRC_ADAPT_V3") ? atoi(getenv("TRC_ADAPT_V3")) : 1;   // 0: previous generation of the adaptive byte rANS kernels (A/B runs)
 static unsigned long long g_launches = 0;       // kernels launched by this library (bench.py reports the delta)
 
@@ -49,7 +50,7 @@ static inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 struct Plan {
     Geom g; int codec;
     size_t slot_stride, rec_stride, o1_threads;
-    size_t off_meta, off_calls, off_slots, off_recs, off_o1, off_tabs, total;
+    size_t off_meta, off_calls, off_slots, off_recs, off_o1, off_tabs, off_lb, total;
 };
 
 // tables needed for n calls when `cpc` consecutive calls share one (0 = one table for everything)
@@ -105,6 +106,7 @@ static int make_plan(int codec, size_t total_len, size_t chunk_len, Plan &p) {
     p.off_o1 = o;    o += al256(p.o1_threads * O1_TAB_WORDS * 4);
     // room for one TableSet per V2_NT calls is the worst case the v2 path accepts (cpc >= V2_NT)
     p.off_tabs = o;  o += codec_static(codec) ? al256(((p.g.n_calls + V2_NT - 1) / V2_NT) * sizeof(TableSet)) : 0;
+    p.off_lb = o;    o += codec == RCS2 ? al256((p.g.n_calls / (LPC_NT / 2) + 2) * 8) : 0;   // look-back words of the fused encoder
     p.total = o;
     return TRC_OK;
 }
@@ -213,9 +215,20 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     const bool v2 = codec_static(codec) && v2_ok(d_in, chunk_len, chunks_per_cdf);
     if (codec == ANSW && !(((uintptr_t)d_in & 3) == 0 && (chunks_per_cdf == 0 || chunks_per_cdf % V2_NT == 0))) return TRC_E_ARG;
     TableSet *tabs = (TableSet *)(sc + p.off_tabs);
-    if (v2 || codec == ANSW) {   // symbol tables once per launch
-        k_build_tables<<<dim3((unsigned)n_tables(g.n_calls, chunks_per_cdf), 1), 256, 0, st>>>(d_cdf, cdfnum, tabs, 0);
+    const bool fused = g_fused && codec == RCS2 && v2 && chunks_per_cdf == 0;
+    unsigned f_cpcta = 0, f_ctas = 0;
+    if (fused) lpc_shape(g.n_calls, 0, f_cpcta, f_ctas);
+    if (v2 || codec == ANSW) {   // symbol tables once per launch (+ the look-back words of the fused encoder)
+        k_build_tables<<<dim3((unsigned)n_tables(g.n_calls, chunks_per_cdf), 1), 256, 0, st>>>(d_cdf, cdfnum, tabs, 0,
+            fused ? (unsigned long long *)(sc + p.off_lb) : nullptr, f_ctas);
         CK_LAUNCH();
+    }
+    if (fused) {                 // coder + offsets + layout in ONE kernel
+        prof_mark(st);
+        k_rcs2_enc_fused<<<f_ctas, (2 * f_cpcta + 31) & ~31u, 0, st>>>(d_in, g, g.n_calls, tabs, slots, p.slot_stride, f_cpcta,
+            (volatile unsigned long long *)(sc + p.off_lb), d_out_off, d_out);
+        CK_LAUNCH(); prof_mark(st); prof_mark(st); prof_mark(st);
+        return TRC_OK;
     }
     const unsigned v2nt = v2_shape(g.n_calls, chunks_per_cdf);
     prof_mark(st);

@@ -166,4 +166,36 @@ __device__ inline void group_copy(uint8_t *dst, const uint8_t *src, size_t n, un
     if (tid < n - done) dst[done + tid] = src[done + tid];
 }
 
+// group_copy for word-aligned pieces with FOUR 16-byte chunks in flight per thread: used where only a few warps copy (the
+// layout epilogue of the fused encoder), so memory-level parallelism has to come from each thread
+__device__ inline void group_copy4(uint8_t *dst, const uint8_t *src, size_t n, unsigned tid, unsigned nthr) {
+    if ((((uintptr_t)dst | (uintptr_t)src) & 3) || n < 256) { group_copy(dst, src, n, tid, nthr); return; }
+    const size_t headw = ((16 - ((uintptr_t)dst & 15)) & 15) >> 2;                  // words until dst is 16-byte aligned
+    if (tid < headw) ((uint32_t *)dst)[tid] = ((const uint32_t *)src)[tid];
+    const uint32_t *s = (const uint32_t *)src + headw;
+    uint4 *d16 = (uint4 *)((uint32_t *)dst + headw);
+    const size_t nw = (n >> 2) - headw, nv = nw >> 2;
+    const unsigned mis = (unsigned)(((uintptr_t)s & 15) >> 2);
+    const uint4 *s16 = (const uint4 *)((uintptr_t)s & ~(uintptr_t)15);
+    auto rot = [&](const uint4 &lo, const uint4 &hi) -> uint4 {
+        if (mis == 0) return lo;
+        if (mis == 1) return make_uint4(lo.y, lo.z, lo.w, hi.x);
+        if (mis == 2) return make_uint4(lo.z, lo.w, hi.x, hi.y);
+        return make_uint4(lo.w, hi.x, hi.y, hi.z);
+    };
+    size_t i = tid;
+    for (; i + 3 * (size_t)nthr < nv; i += 4 * (size_t)nthr) {
+        uint4 lo[4], hi[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { lo[k] = s16[i + k * nthr]; hi[k] = mis ? s16[i + k * nthr + 1] : lo[k]; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) d16[i + k * nthr] = rot(lo[k], hi[k]);
+    }
+    for (; i < nv; i += nthr) { const uint4 lo = s16[i], hi = mis ? s16[i + 1] : lo; d16[i] = rot(lo, hi); }
+    const size_t donew = headw + (nv << 2), totw = n >> 2;
+    if (donew + tid < totw) ((uint32_t *)dst)[donew + tid] = ((const uint32_t *)src)[donew + tid];   // < 4 tail words
+    const size_t doneb = totw << 2;
+    if (tid < n - doneb) dst[doneb + tid] = src[doneb + tid];
+}
+
 }  // namespace trc
