@@ -290,3 +290,19 @@ def test_wide_rans_answ(trc, port, dg):
     assert np.array_equal(trc.dec_batch_host(trc.ANSW, got, goff, d.size, 65536, cdf=cdf, cdfnum=256), d)
     with pytest.raises(trc.TrcError):                      # our own format: calls must start 4-byte aligned
         trc.enc_batch_host(trc.ANSW, d[:10_000], 1001, cdf=cdf, cdfnum=256)
+
+
+@pytest.mark.gpu
+def test_fused_encoder_many_waves(trc, port, dg):
+    """k_rcs2_enc_fused on a grid of several waves (262 144 calls -> 4096 CTAs): offsets from the decoupled look-back and the
+    in-kernel layout must equal the reference calls packed back to back."""
+    d = dg.zipf(32 << 20, seed=21)
+    cdf = port.cdfini(d)
+    chunk = 128
+    got, off = trc.enc_batch_host(trc.RCS2, d, chunk, cdf=cdf, cdfnum=256)
+    want, woff = cpu_batch(port, trc.RCS2, d[:1 << 20], chunk, cdf, 256)           # the oracle on the first 8192 calls ...
+    k = (1 << 20) // chunk
+    assert np.array_equal(off[:k + 1], woff) and np.array_equal(got[:int(woff[-1])], want)
+    assert np.all(np.diff(off.astype(np.int64)) > 0) and int(off[-1]) == got.size    # ... and every call through its round trip
+    back = trc.dec_batch_host(trc.RCS2, got, off, d.size, chunk, cdf=cdf, cdfnum=256)
+    assert np.array_equal(back, d)

@@ -569,11 +569,18 @@ k_rcs2_enc_fused(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const T
     constexpr int NW = LPC_MAX_NT / 32;                        // warp sums; [NW] = the CTA aggregate
     __shared__ uint32_t s_wsum[NW + 1];
     __shared__ unsigned long long s_base;
-    const size_t j0 = (size_t)blockIdx.x * calls_per_cta, j = j0 + (threadIdx.x >> 1);
-    const unsigned c = threadIdx.x & 1, r = threadIdx.x >> 1;
-    if (threadIdx.x == 0) tma_fetch(ctab, ts->ctab, sizeof ctab, &bar);
+    // tile index in ARRIVAL order (lb[gridDim.x] is a counter): a CTA only ever waits for tiles that already run, whatever
+    // order the hardware starts CTAs in -- the look-back cannot deadlock on grids of more than one wave
+    __shared__ unsigned s_tile;
+    if (threadIdx.x == 0) {
+        s_tile = (unsigned)atomicAdd((unsigned long long *)(lb + gridDim.x), 1ull);
+        tma_fetch(ctab, ts->ctab, sizeof ctab, &bar);
+    }
     __syncthreads();
     tma_wait(&bar);
+    const unsigned bid = s_tile;
+    const size_t j0 = (size_t)bid * calls_per_cta, j = j0 + (threadIdx.x >> 1);
+    const unsigned c = threadIdx.x & 1, r = threadIdx.x >> 1;
     const bool live = j < n_calls && r < calls_per_cta;
     size_t start = 0, n = 0;
     if (live) call_span(g, j, start, n);
@@ -638,10 +645,10 @@ k_rcs2_enc_fused(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const T
     // ---- decoupled look-back for the CTA's base offset
     if (wid == 0) {
         const unsigned long long agg = s_wsum[NW];
-        if (lane == 0) { lb[blockIdx.x] = (blockIdx.x == 0 ? LB_INC : LB_AGG) | agg; __threadfence(); }
+        if (lane == 0) { lb[bid] = (bid == 0 ? LB_INC : LB_AGG) | agg; __threadfence(); }
         unsigned long long base = 0;
-        if (blockIdx.x) {
-            long long idx = (long long)blockIdx.x - 1;
+        if (bid) {
+            long long idx = (long long)bid - 1;
             for (;;) {
                 const long long k = idx - lane;
                 unsigned long long st = LB_INC;                   // before CTA 0: inclusive prefix 0
@@ -655,7 +662,7 @@ k_rcs2_enc_fused(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const T
                 if (incl) break;
                 idx -= 32;
             }
-            if (lane == 0) { lb[blockIdx.x] = LB_INC | (base + agg); __threadfence(); }
+            if (lane == 0) { lb[bid] = LB_INC | (base + agg); __threadfence(); }
         }
         if (lane == 0) s_base = base;
     }

@@ -106,7 +106,7 @@ static int make_plan(int codec, size_t total_len, size_t chunk_len, Plan &p) {
     p.off_o1 = o;    o += al256(p.o1_threads * O1_TAB_WORDS * 4);
     // room for one TableSet per V2_NT calls is the worst case the v2 path accepts (cpc >= V2_NT)
     p.off_tabs = o;  o += codec_static(codec) ? al256(((p.g.n_calls + V2_NT - 1) / V2_NT) * sizeof(TableSet)) : 0;
-    p.off_lb = o;    o += codec == RCS2 ? al256((p.g.n_calls / (LPC_NT / 2) + 2) * 8) : 0;   // look-back words of the fused encoder
+    p.off_lb = o;    o += codec == RCS2 ? al256((p.g.n_calls / (LPC_NT / 2) + 3) * 8) : 0;   // look-back words of the fused encoder + tile counter
     p.total = o;
     return TRC_OK;
 }
@@ -220,7 +220,7 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     if (fused) lpc_shape(g.n_calls, 0, f_cpcta, f_ctas);
     if (v2 || codec == ANSW) {   // symbol tables once per launch (+ the look-back words of the fused encoder)
         k_build_tables<<<dim3((unsigned)n_tables(g.n_calls, chunks_per_cdf), 1), 256, 0, st>>>(d_cdf, cdfnum, tabs, 0,
-            fused ? (unsigned long long *)(sc + p.off_lb) : nullptr, f_ctas);
+            fused ? (unsigned long long *)(sc + p.off_lb) : nullptr, f_ctas + 1);
         CK_LAUNCH();
     }
     if (fused) {                 // coder + offsets + layout in ONE kernel
