@@ -46,6 +46,7 @@ REF_FN = {0: ("anscdf4senc", "anscdf4sdec"), 1: ("anscdf4enc", "anscdf4dec"), 2:
           19: ("rccdfvenc16", "rccdfvdec16"), 20: ("rccdfvzenc16", "rccdfvzdec16"), 21: ("rccdfvenc32", "rccdfvdec32"),
           22: ("rccdfvzenc32", "rccdfvzdec32"), 23: ("rccdfuenc16", "rccdfudec16"), 24: ("rccdfuenc32", "rccdfudec32"),
           10: ("answenc", "answdec")}       # this repository's 32-way interleaved static rANS: no reference function, CPU leg = oracle port
+CALLS_PER_SM = 384     # resident reference calls per SM in one wave of k_rcs2_enc_fused / k_rcs2_dec_lpc (2 CTAs x 192 calls x 2 lanes)
 METRIC = "encode+decode GB/s on 100MB order-0 byte stream; bitstream bit-exact vs ref"
 SRC_NAME = {"zipf": "Zipf(1.1)", "bwt": "BWT-shaped", "o1": "order-1 Markov", "uniform": "uniform random"}
 
@@ -174,6 +175,13 @@ def run_ours(args):
     trc.lib.trc_set_device(local)
     codec = CODECS[args.codec]
     size, chunk = args.size, args.chunk
+    auto_chunk = chunk == 0
+    if auto_chunk:
+        # one balanced wave of coder chains: the lane-per-coder kernels keep 384 calls (768 lanes at 78-80 registers) resident
+        # per SM; the chunk size is the largest multiple of 16 that gives every SM that many calls of this buffer
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        chunk = -(-size // (n_sm * CALLS_PER_SM)) if args.codec == "rcs2" else 4096
+        chunk = min(65536, max(256, (chunk + 15) & ~15))
     static = codec in (0, 4, 5, 10)
 
     data = make_data(size, rank, args.src)
@@ -365,7 +373,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"{size} B {SRC_NAME[args.src]} bytes per GPU, " + (("static CDF (cdfini per " + (str(args.cdf_block) + "-byte block" if args.cdf_block else "whole buffer") + "), ") if static else "adaptive model, ") +
                                    f"batch of {chunk}-byte chunks, each chunk == one reference call ({REF_FN[codec][0]}/{REF_FN[codec][1]})",
-                       "codec": args.codec, "chunk_bytes": chunk, "n_chunks": n_chunks, "l2": "flushed (256 MiB write) before each timed encode and decode",
+                       "codec": args.codec, "chunk_bytes": chunk, "chunk_choice": ("one wave: %d calls per SM" % CALLS_PER_SM) if auto_chunk else "--chunk", "n_chunks": n_chunks, "l2": "flushed (256 MiB write) before each timed encode and decode",
                        "multi_gpu": f"independent shard per rank, packed streams gathered on rank 0 inside the step: {gather_kind}" if world > 1 else "single GPU"},
             "enc_gbs": round(total_bytes / (enc_ms * 1e-3) / 1e9, 3), "dec_gbs": round(total_bytes / (dec_ms * 1e-3) / 1e9, 3),
             "ratio": round(clen / size, 5), "compressed_bytes": int(clen),
@@ -384,7 +392,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--codec", default="rcs2", choices=sorted(CODECS))
-    ap.add_argument("--chunk", type=int, default=2048, help="bytes per reference call (2 KiB: twice the coder chains of 4 KiB, +0.2 %% compressed size; DESIGN.md section 5)")
+    ap.add_argument("--chunk", type=int, default=0, help="bytes per reference call; 0 = size the batch to one balanced wave (384 calls per SM: 1760 B for 100 MB on 148 SMs; DESIGN.md section 5)")
     ap.add_argument("--size", type=int, default=100_000_000)
     ap.add_argument("--bytes-alphabet", action="store_true", help="ans4s: code full bytes with a 256-entry table")
     ap.add_argument("--src", default="zipf", choices=["zipf", "bwt", "o1", "uniform"], help="synthetic source (SURVEY.md section 8d)")
