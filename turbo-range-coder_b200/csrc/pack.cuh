@@ -112,7 +112,14 @@ k_push(uint4 *__restrict__ dst, const uint4 *__restrict__ src, const uint64_t *_
        uint64_t *__restrict__ dst_len) {
     const uint64_t len = d_len ? *d_len : (uint64_t)fixed_len;
     const size_t nv = (size_t)((len + 15) >> 4), stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) dst[i] = src[i];
+    // four 16-byte chunks in flight per thread: the kernel runs on a few CTAs next to the decoder, so the bandwidth over
+    // NVLink has to come from memory-level parallelism per thread, not from thread count
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < nv; i += 4 * stride) {
+        const uint4 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+        dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    }
+    for (; i < nv; i += stride) dst[i] = src[i];
     if (dst_len && blockIdx.x == 0 && threadIdx.x == 0) *dst_len = len;
 }
 
