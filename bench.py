@@ -169,6 +169,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # the version banner goes to stdout, where only the JSON line belongs
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     trc = importlib.import_module("turbo-range-coder_b200")
     shard = importlib.import_module("turbo-range-coder_b200.shard")
