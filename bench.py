@@ -46,7 +46,8 @@ REF_FN = {0: ("anscdf4senc", "anscdf4sdec"), 1: ("anscdf4enc", "anscdf4dec"), 2:
           19: ("rccdfvenc16", "rccdfvdec16"), 20: ("rccdfvzenc16", "rccdfvzdec16"), 21: ("rccdfvenc32", "rccdfvdec32"),
           22: ("rccdfvzenc32", "rccdfvzdec32"), 23: ("rccdfuenc16", "rccdfudec16"), 24: ("rccdfuenc32", "rccdfudec32"),
           10: ("answenc", "answdec")}       # this repository's 32-way interleaved static rANS: no reference function, CPU leg = oracle port
-CALLS_PER_SM = 384     # resident reference calls per SM in one wave of k_rcs2_enc_fused / k_rcs2_dec_lpc (2 CTAs x 192 calls x 2 lanes)
+CALLS_PER_SM = 384     # resident reference calls per SM in one wave of the lane-per-coder rcs2 kernels (2 CTAs x 192 calls x 2 lanes)
+B200_SMS = 148         # the default chunk is sized for this part; both arms derive it from the same constants (no device query)
 METRIC = "encode+decode GB/s on 100MB order-0 byte stream; bitstream bit-exact vs ref"
 SRC_NAME = {"zipf": "Zipf(1.1)", "bwt": "BWT-shaped", "o1": "order-1 Markov", "uniform": "uniform random"}
 
@@ -101,8 +102,44 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted({norm.get(r, r) for r in self.reasons} - {"gpu_idle"})}
 
 
+def datagen():
+    """datagen.py loaded by path: importing the package would dlopen libtrc_b200.so, which the reference arm must not do."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("trc_datagen", os.path.join(ROOT, "turbo-range-coder_b200", "datagen.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def default_chunk(args):
+    """--chunk 0: one balanced wave of coder chains on a B200 (CALLS_PER_SM reference calls per SM), a multiple of 16 bytes."""
+    if args.chunk:
+        return args.chunk
+    chunk = -(-args.size // (B200_SMS * CALLS_PER_SM)) if args.codec == "rcs2" else 4096
+    return min(65536, max(256, (chunk + 15) & ~15))
+
+
+def workload_config(args, chunk, world):
+    """`config` of the JSON line -- built by ONE function so that both arms (ours / --impl reference) name the same workload."""
+    codec = CODECS[args.codec]
+    static = codec in (0, 4, 5, 10)
+    n_chunks = -(-args.size // chunk)
+    tab = ("static CDF (cdfini per " + (str(args.cdf_block) + "-byte block" if args.cdf_block else "whole buffer") + "), ") if static else "adaptive model, "
+    return {"workload": f"{args.size} B {SRC_NAME[args.src]} bytes per GPU, {tab}batch of {chunk}-byte chunks, "
+                        f"each chunk == one reference call ({REF_FN[codec][0]}/{REF_FN[codec][1]})",
+            "codec": args.codec, "chunk_bytes": chunk, "n_chunks": n_chunks,
+            "chunk_choice": ("one wave on %d SMs: %d calls per SM" % (B200_SMS, CALLS_PER_SM)) if not args.chunk else "--chunk",
+            "l2": "GPU arm: flushed (256 MiB write) before each timed encode and decode; CPU arm: 100 MB working set >> host LLC",
+            "multi_gpu": (f"independent {args.size}-byte shard per rank, packed streams gathered on rank 0 inside the step" if world > 1 else "single GPU")}
+
+
+def sha16(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
 def make_data(size, rank=0, src="zipf"):
-    dg = importlib.import_module("turbo-range-coder_b200.datagen")
+    dg = datagen()
     if src == "bwt":
         return dg.bwt_shaped(size, seed=dg.BWT_SEED + rank)
     if src == "o1":
@@ -112,50 +149,146 @@ def make_data(size, rank=0, src="zipf"):
     return dg.zipf(size, seed=dg.ZIPF_SEED + rank)
 
 
-def cpu_reference_run(codec, data, cdf, threads, reps, sample_bytes):
+def cpu_reference_run(codec, data, cdf, threads, reps, sample_bytes, chunk, cpc=0):
+    """Time the reference encoder + decoder (oracle/_ref, else the port) called once per `chunk`-byte chunk on `threads` pthreads."""
     from oracle import cpu
     enc, dec = REF_FN[codec]
     sample = data[:sample_bytes]
-    r = cpu.cpu_bench(codec != 10, enc, dec, sample, 4 << 20, cdf if codec in (0, 4, 5, 10) else None, 256 if codec in (4, 5, 10) else 0,
+    r = cpu.cpu_bench(codec != 10, enc, dec, sample, chunk, cdf if codec in (0, 4, 5, 10) else None, 256 if codec in (4, 5, 10) else 0,
                       threads=threads, reps=reps)
     r["sample_bytes"] = int(sample.size)
     return r
 
 
+def oracle_stream(codec, data, chunk, cdf, cpc=0):
+    """The packed stream the CHECKER produces for this batch (compiled reference when present, else the port)."""
+    from oracle import cpu
+    lib = (cpu.ref() if codec != 10 else None) or cpu.port()
+    static = codec in (0, 4, 5, 10)
+    return cpu.batch_enc(lib, REF_FN[codec][0], data, chunk, cdf if static else None, 256 if codec in (4, 5, 10) else (16 if codec == 0 else 0), cpc)
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation on all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path on all host threads, on the SAME workload as our
+    arm (same bytes, same table, same chunking => the same packed stream: size and hash are printed by both arms)."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
     from oracle import cpu
     codec = CODECS[args.codec]
+    chunk = default_chunk(args)
+    static = codec in (0, 4, 5, 10)
     threads = os.cpu_count() or 1
-    sample_bytes = min(args.size, (8 << 20) * threads)
-    data = make_data(sample_bytes, 0, args.src)
+    data = make_data(args.size, 0, args.src)                     # rank 0's shard: CPU throughput does not depend on the shard count
+    if codec in (0, 1, 8, 9) and not (codec == 0 and args.bytes_alphabet):
+        data = data & 15
     lib = cpu.ref() or cpu.port()
-    cdf = lib.cdfini(data)
-    for _ in range(max(args.warmup, 1)):
-        r = cpu_reference_run(codec, data, cdf, threads, 1, sample_bytes)
+    cdf = None
+    if static:
+        blk = args.cdf_block if args.cdf_block else args.size
+        cdf = np.concatenate([lib.cdfini(data[o:o + blk]) for o in range(0, args.size, blk)])
+    if args.cdf_block:
+        raise SystemExit("--impl reference: per-block tables are not wired into the timing driver")
+    for _ in range(max(min(args.warmup, 3), 1)):
+        r = cpu_reference_run(codec, data, cdf, threads, 1, args.size, chunk)
     es = ds = 0.0
-    args.steps = min(args.steps, 20)             # each step is ~0.2-0.5 s of CPU work on the bounded sample; keep the arm to minutes
-    for _ in range(args.steps):
-        r = cpu_reference_run(codec, data, cdf, threads, 1, sample_bytes)
+    for _ in range(args.steps):                                  # one step = the whole workload: ~0.3 s (rcs2, 16 threads)
+        r = cpu_reference_run(codec, data, cdf, threads, 1, args.size, chunk)
         assert r["ok"], "reference round trip failed"
         es += r["enc_s"]; ds += r["dec_s"]
     es /= args.steps; ds /= args.steps
-    val = sample_bytes / (es + ds) / 1e9
-    sample = (f"first {sample_bytes} B of the workload, {REF_FN[codec][0]}+{REF_FN[codec][1]} called per 4 MiB chunk, "
+    stream, off = oracle_stream(codec, data, chunk, cdf)
+    assert stream.size == r["clen"]
+    val = args.size / (es + ds) / 1e9
+    sample = (f"the whole workload ({args.size} B), {REF_FN[codec][0]}+{REF_FN[codec][1]} called once per {chunk}-byte chunk, "
               f"{threads} pthreads, mean of {args.steps} passes")
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 4), "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round((es + ds) * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{args.size} B {SRC_NAME[args.src]} bytes, codec {args.codec}", "codec": args.codec},
-            "enc_gbs": round(sample_bytes / es / 1e9, 4), "dec_gbs": round(sample_bytes / ds / 1e9, 4),
-            "ratio": round(r["clen"] / sample_bytes, 5),
+            "config": workload_config(args, chunk, world),
+            "enc_gbs": round(args.size / es / 1e9, 4), "dec_gbs": round(args.size / ds / 1e9, 4),
+            "ratio": round(r["clen"] / args.size, 5), "compressed_bytes": int(r["clen"]), "stream_sha16": sha16(stream),
             "cpu_baseline": {"value": round(val, 4), "unit": "GB/s", "cores": threads, "kind": r["kind"], "sample": sample},
             "e2e": {"value": round(val, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
+
+
+def markov1_dev(torch, n, dev, seed=20261019, lanes=1 << 18):
+    """BASELINE config 4 source generated ON THE DEVICE (1 GB from numpy takes ~100 s): the same order-1 process as
+    datagen.markov1 -- rank ~ Zipf(1.1), byte = perm[prev][rank], 256 fixed permutations -- run as `lanes` independent chains
+    laid end to end.  Deterministic for a given torch build; the oracle checks the very bytes that are coded."""
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    k = torch.arange(1, 257, dtype=torch.float64, device=dev)
+    cdf = torch.cumsum(k ** -1.1, 0); cdf = (cdf / cdf[-1]).to(torch.float32)
+    perms = torch.stack([torch.randperm(256, generator=g, device=dev) for _ in range(256)]).to(torch.uint8)
+    per = -(-n // lanes)
+    out = torch.empty(lanes * per, dtype=torch.uint8, device=dev).view(lanes, per)
+    prev = torch.zeros(lanes, dtype=torch.long, device=dev)
+    step = 4096
+    for j0 in range(0, per, step):
+        w = min(step, per - j0)
+        ranks = torch.searchsorted(cdf, torch.rand(lanes, w, generator=g, device=dev)).clamp_(max=255)
+        for j in range(w):
+            v = perms[prev, ranks[:, j]]
+            out[:, j0 + j] = v
+            prev = v.long()
+    return out.view(-1)[:n].contiguous()
+
+
+def time_batch(trc, torch, batch, d_in, flush, steps, warmup=2):
+    """-> (encode ms, decode ms) per pass: CUDA events on the launching stream, L2 flushed before each timed pass."""
+    for _ in range(warmup):
+        batch.encode(d_in); batch.decode()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    for k in range(steps):
+        flush.zero_(); ev[k][0].record(); batch.encode(d_in); ev[k][1].record()
+        flush.zero_(); ev[k][2].record(); batch.decode(); ev[k][3].record()
+    torch.cuda.synchronize()
+    return sum(e[0].elapsed_time(e[1]) for e in ev) / steps, sum(e[2].elapsed_time(e[3]) for e in ev) / steps
+
+
+def run_extras(trc, torch, dev, d_zipf, cdf_dev, flush, main_chunk):
+    """Extra keys of the JSON line (not the headline): the chunk-size curve of the headline codec and the adaptive / order-1
+    configurations of BASELINE.json (configs[2], configs[3]) at their full sizes, each with a device round trip and the packed
+    stream compared with the oracle's."""
+    out = {}
+    size = d_zipf.numel()
+    sweep = []
+    for chunk in sorted({main_chunk, 4096, 65536, 1 << 20}):
+        b = trc.DeviceBatch(CODECS["rcs2"], size, chunk, cdfnum=256, device=dev)
+        b.cdf = cdf_dev
+        b.encode(d_zipf); back = b.decode(); torch.cuda.synchronize()
+        assert torch.equal(back, d_zipf)
+        e, d = time_batch(trc, torch, b, d_zipf, flush, 3 if chunk >= 65536 else 10)
+        sweep.append({"chunk_bytes": chunk, "n_chunks": b.n, "enc_gbs": round(size / e / 1e6, 2), "dec_gbs": round(size / d / 1e6, 2),
+                      "value": round(size / (e + d) / 1e6, 2), "ratio": round(b.compressed_len() / size, 5)})
+        del b
+    out["chunk_sweep"] = {"codec": "rcs2", "workload": f"{size} B Zipf(1.1), one table", "unit": "GB/s", "points": sweep}
+
+    def adaptive(name, d_in, chunk, steps, src):
+        n = d_in.numel()
+        codec = CODECS[name]
+        b = trc.DeviceBatch(codec, n, chunk, device=dev)
+        b.encode(d_in); back = b.decode(); torch.cuda.synchronize()
+        assert torch.equal(back, d_in), f"{name}: device round trip failed"
+        clen = b.compressed_len()
+        want, woff = oracle_stream(codec, d_in.cpu().numpy(), chunk, None)
+        ok = bool(np.array_equal(b.off.cpu().numpy().view(np.uint64), woff) and np.array_equal(b.out[:clen].cpu().numpy(), want))
+        assert ok, f"{name}: packed stream differs from the oracle's"
+        e, d = time_batch(trc, torch, b, d_in, flush, steps, warmup=1)
+        return {"workload": f"{n} B {src}, {REF_FN[codec][0]}/{REF_FN[codec][1]} once per {chunk}-byte chunk", "codec": name, "chunk_bytes": chunk,
+                "value": round(n / (e + d) / 1e6, 3), "unit": "GB/s", "enc_gbs": round(n / e / 1e6, 3), "dec_gbs": round(n / d / 1e6, 3),
+                "ratio": round(clen / n, 5), "steps": steps, "stream_equals_oracle": ok,
+                "roofline_frac": round((n + clen) / (max(e, d) * 1e-3) / 1e9 / peaks()[0], 5)}
+
+    bwt = torch.from_numpy(make_data(size, 0, "bwt")).to(dev)
+    out["config3_adaptive_bwt_100mb"] = [adaptive("rc", bwt, 65536, 3, "BWT-shaped bytes"), adaptive("ans", bwt, 65536, 3, "BWT-shaped bytes")]
+    del bwt
+    o1 = markov1_dev(torch, 1_000_000_000, dev)
+    out["config4_order1_1gb"] = adaptive("ans1", o1, 4 << 20, 2, "order-1 Markov bytes (generated on the device, bench.py markov1_dev)")
+    return out
 
 
 def run_ours(args):
@@ -176,14 +309,7 @@ def run_ours(args):
     shard = importlib.import_module("turbo-range-coder_b200.shard")
     trc.lib.trc_set_device(local)
     codec = CODECS[args.codec]
-    size, chunk = args.size, args.chunk
-    auto_chunk = chunk == 0
-    if auto_chunk:
-        # one balanced wave of coder chains: the lane-per-coder kernels keep 384 calls (768 lanes at 78-80 registers) resident
-        # per SM; the chunk size is the largest multiple of 16 that gives every SM that many calls of this buffer
-        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        chunk = -(-size // (n_sm * CALLS_PER_SM)) if args.codec == "rcs2" else 4096
-        chunk = min(65536, max(256, (chunk + 15) & ~15))
+    size, chunk = args.size, default_chunk(args)
     static = codec in (0, 4, 5, 10)
 
     data = make_data(size, rank, args.src)
@@ -200,13 +326,24 @@ def run_ours(args):
         batch.cpc = blk // chunk if args.cdf_block else 0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    # ---- correctness gate (untimed): round trip on the device, packed stream vs the oracle on a bounded prefix ----
+    # ---- correctness gate (untimed): device round trip, and the WHOLE packed stream + offsets byte-compared with what the
+    # checker (compiled reference, else the port) produces for the same chunks -- at the chunk size that is timed below
     batch.encode(d_in)
     back = batch.decode()
     torch.cuda.synchronize()
     assert torch.equal(back, d_in), "device round trip failed"
     clen = batch.compressed_len()
     n_chunks = batch.n
+    stream_sha = None
+    if not args.no_gate:
+        cdf_gate = batch.cdf.cpu().numpy().view(np.uint16) if static else None
+        want, woff = oracle_stream(codec, data, chunk, cdf_gate, batch.cpc)
+        got = batch.out[:clen].cpu().numpy()
+        goff = batch.off.cpu().numpy().view(np.uint64)
+        assert np.array_equal(goff, woff), "packed offsets differ from the oracle's"
+        assert np.array_equal(got, want), "packed stream differs from the oracle's"
+        stream_sha = sha16(got)
+        del want, got
 
     # multi-GPU: the packed streams are gathered on rank 0 inside every step.  Default: device-driven push over NVLink
     # peer memory (shard.PeerGather) on a side stream, overlapping the decode; TRC_GATHER=nccl selects the NCCL
@@ -360,27 +497,33 @@ def run_ours(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        sample_bytes = min(size, (8 << 20) * threads)
-        from oracle import cpu
-        cdfh = (cpu.ref() or cpu.port()).cdfini(data[:sample_bytes]) if static else None     # (one table for the CPU sample)
-        r = cpu_reference_run(codec, data, cdfh, threads, 2, sample_bytes)
-        one = cpu_reference_run(codec, data, cdfh, 1, 1, min(sample_bytes, 16 << 20))
-        cpu_baseline = {"value": round(sample_bytes / (r["enc_s"] + r["dec_s"]) / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": r["kind"],
-                        "sample": f"first {sample_bytes} B of the workload, {REF_FN[codec][0]}+{REF_FN[codec][1]} per 4 MiB chunk, {threads} pthreads, best of 2",
-                        "enc_gbs": round(sample_bytes / r["enc_s"] / 1e9, 4), "dec_gbs": round(sample_bytes / r["dec_s"] / 1e9, 4),
+        cdfh = batch.cdf.cpu().numpy().view(np.uint16)[:257].copy() if static else None      # the same table the GPU used
+        r = cpu_reference_run(codec, data, cdfh, threads, 2, size if not args.cdf_block else min(size, args.cdf_block), chunk)
+        one = cpu_reference_run(codec, data, cdfh, 1, 1, min(size, 16 << 20), chunk)
+        sb = r["sample_bytes"]
+        cpu_baseline = {"value": round(sb / (r["enc_s"] + r["dec_s"]) / 1e9, 4), "unit": "GB/s", "cores": threads, "kind": r["kind"],
+                        "sample": f"first {sb} B of the workload, {REF_FN[codec][0]}+{REF_FN[codec][1]} once per {chunk}-byte chunk, {threads} pthreads, best of 2",
+                        "enc_gbs": round(sb / r["enc_s"] / 1e9, 4), "dec_gbs": round(sb / r["dec_s"] / 1e9, 4),
                         "single_thread_gbs": round(one["sample_bytes"] / (one["enc_s"] + one["dec_s"]) / 1e9, 4)}
 
+    extras = None
+    if world == 1 and not args.no_extras and args.codec == "rcs2" and args.src == "zipf" and size == 100_000_000 and not args.cdf_block:
+        extras = run_extras(trc, torch, dev, d_in, batch.cdf, flush, chunk)
+
+    cfg = workload_config(args, chunk, world)
+    if world > 1:
+        cfg["multi_gpu"] += ": " + gather_kind
     line = {"metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(step_ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": f"{size} B {SRC_NAME[args.src]} bytes per GPU, " + (("static CDF (cdfini per " + (str(args.cdf_block) + "-byte block" if args.cdf_block else "whole buffer") + "), ") if static else "adaptive model, ") +
-                                   f"batch of {chunk}-byte chunks, each chunk == one reference call ({REF_FN[codec][0]}/{REF_FN[codec][1]})",
-                       "codec": args.codec, "chunk_bytes": chunk, "chunk_choice": ("one wave: %d calls per SM" % CALLS_PER_SM) if auto_chunk else "--chunk", "n_chunks": n_chunks, "l2": "flushed (256 MiB write) before each timed encode and decode",
-                       "multi_gpu": f"independent shard per rank, packed streams gathered on rank 0 inside the step: {gather_kind}" if world > 1 else "single GPU"},
+            "config": cfg,
             "enc_gbs": round(total_bytes / (enc_ms * 1e-3) / 1e9, 3), "dec_gbs": round(total_bytes / (dec_ms * 1e-3) / 1e9, 3),
-            "ratio": round(clen / size, 5), "compressed_bytes": int(clen),
+            "ratio": round(clen / size, 5), "compressed_bytes": int(clen), "stream_sha16": stream_sha,
+            "gate": "whole packed stream + offsets byte-compared with the oracle's at this chunk size" if stream_sha else "device round trip only (--no-gate)",
             "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
+    if extras:
+        line.update(extras)
     print(json.dumps(line))
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
@@ -400,6 +543,8 @@ def main():
     ap.add_argument("--src", default="zipf", choices=["zipf", "bwt", "o1", "uniform"], help="synthetic source (SURVEY.md section 8d)")
     ap.add_argument("--cdf-block", type=int, default=0, help="static codecs: one cdfini table per this many bytes (0 = whole buffer)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-gate", action="store_true", help="skip the oracle comparison of the packed stream (device round trip only)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the chunk sweep and the BASELINE config 3/4 lines (extra keys of the JSON line)")
     args = ap.parse_args()
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 

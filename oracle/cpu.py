@@ -178,3 +178,32 @@ def cpu_bench(use_ref, enc, dec, data, chunk, cdf=None, cdfnum=0, threads=None, 
     if rc:
         raise RuntimeError(f"orc_cpu_bench failed: {rc}")
     return dict(enc_s=es.value, dec_s=ds.value, clen=cl.value, ok=bool(ok.value), threads=threads, kind=kind)
+
+
+def batch_enc(lib, enc, data, chunk, cdf=None, cdfnum=0, chunks_per_cdf=0, threads=None):
+    """The checker's statement of the batch layer: `enc` called once per chunk by `threads` host threads, results packed
+    back to back (oracle/cpu_bench.c orc_batch_enc).  `lib` = port() or ref().  -> (packed bytes, offsets[n+1])."""
+    p = os.path.join(_HERE, "libtrc_cpubench.so")
+    if not os.path.exists(p):
+        build(ref_too=False)
+    drv = ctypes.CDLL(p)
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    n = -(-data.size // chunk)
+    sig = 2 if ENCODERS[enc][1] else (1 if ENCODERS[enc][0] else 0)
+    tabs = None
+    if cdf is not None:
+        tabs = np.ascontiguousarray(cdf, dtype=np.uint16).reshape(-1)
+        nt = -(-n // chunks_per_cdf) if chunks_per_cdf else 1
+        if tabs.size < nt * 257:
+            tabs = np.concatenate([tabs, np.zeros(nt * 257 - tabs.size, np.uint16)])
+    cap = data.size + 4 * n + 64
+    out = np.empty(cap, np.uint8)
+    off = np.zeros(n + 1, np.uint64)
+    drv.orc_batch_enc.restype = ctypes.c_int
+    rc = drv.orc_batch_enc(lib.path.encode(), (lib.prefix + enc).encode(), ctypes.c_int(sig), ctypes.c_void_p(data.ctypes.data),
+                           ctypes.c_size_t(data.size), ctypes.c_size_t(chunk), ctypes.c_void_p(tabs.ctypes.data if tabs is not None else None),
+                           ctypes.c_uint(cdfnum), ctypes.c_size_t(chunks_per_cdf), ctypes.c_int(threads or os.cpu_count() or 1),
+                           ctypes.c_void_p(out.ctypes.data), ctypes.c_size_t(cap), ctypes.c_void_p(off.ctypes.data))
+    if rc:
+        raise RuntimeError(f"orc_batch_enc failed: {rc}")
+    return out[:int(off[n])], off

@@ -5,7 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from helpers import cpu_batch
+from helpers import cpu_batch, CODECS
 
 pytestmark = pytest.mark.gpu
 N = 100_000_000
@@ -33,6 +33,33 @@ def test_config2_static_100mb(trc, port, zipf100):
         assert _sha(got) == _sha(want)
         back = trc.dec_batch_host(codec, got, off, N, 4096, cdf=cdf, cdfnum=256)
         assert _sha(back) == "e9e9669ae62e03c9"
+
+
+def _oracle_batch(port, codec, data, chunk, cdf=None, cdfnum=0):
+    """Checker's packed stream for the batch, multi-threaded (oracle/cpu_bench.c): compiled reference when built, else the port."""
+    from oracle import cpu
+    return cpu.batch_enc(cpu.ref() or port, CODECS[codec][0], data, chunk, cdf, cdfnum)
+
+
+@pytest.mark.parametrize("chunk", ["bench", 65536, 1 << 20])
+def test_headline_chunks_100mb(trc, port, zipf100, chunk):
+    """The configuration bench.py times: TRC_RCS2 over 100 MB Zipf(1.1) at bench.py's default chunk (1760 B on a B200),
+    and at 64 KiB / 1 MiB: packed stream, offsets and round trip against the oracle, byte for byte."""
+    if chunk == "bench":
+        import argparse, os, sys
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
+        chunk = bench.default_chunk(argparse.Namespace(chunk=0, size=N, codec="rcs2"))
+        assert chunk == 1760
+    cdf = trc.cdfini(zipf100)
+    got, off = trc.enc_batch_host(trc.RCS2, zipf100, chunk, cdf=cdf, cdfnum=256)
+    want, woff = _oracle_batch(port, trc.RCS2, zipf100, chunk, cdf, 256)
+    assert np.array_equal(off, woff)
+    assert got.size == want.size and np.array_equal(got, want)
+    if chunk == 1760:
+        assert got.size == 72_551_464                   # the size both bench arms print
+    back = trc.dec_batch_host(trc.RCS2, got, off, N, chunk, cdf=cdf, cdfnum=256)
+    assert _sha(back) == "e9e9669ae62e03c9"
 
 
 def test_config3_adaptive_100mb(trc, port, dg):
