@@ -1,0 +1,339 @@
+// rcs2_v3.cuh -- TRC_RCS2 (rccdfs2enc / rccdfsb2dec, rccdf.c:125-184) headline kernels, third generation.
+//
+// Same mapping as static_v2.cuh's lane-per-coder kernels (lanes 2r / 2r+1 of a warp own coder 0 / coder 1 of call r),
+// rebuilt around what the round-1 profiles and the micro-benchmarks in tools/ubench showed:
+//
+//  * ENCODE was bound by its scattered 4-byte global stores, not by arithmetic (tools/ubench/enc_step.cu: the same step
+//    costs 71 cycles per warp-symbol with stores to the global slot and 38 with stores to shared memory).  Emitted words now
+//    go to an 8-word ring per lane in shared memory (word-major, lane-minor: conflict-free whatever position a lane is at)
+//    and leave as 128-bit stores, four words at a time.
+//  * The coder step keeps `low` as a 96-bit number whose top word is the pending output word, so the carry of
+//    low += range * cdf[x] (turborc_.h:215, _rccarry_ :103) runs straight into the pending word through the add-with-carry
+//    chain: no carry flag, no compare, no select -- 22.5 SASS instructions per symbol instead of 41.  A carry OUT of the
+//    pending word (it held 0xffffffff: the reference would walk back through stored words, p ~ 2^-32 per word) lands in a
+//    fourth chain word; a lane that ever sees one has its call redone by the exact walk-back coder.
+//  * INPUT arrives by TMA: the batch is described as a 2-D tensor [calls][chunk bytes] and every warp pulls the next
+//    128 bytes of its 16 calls with ONE cp.async.bulk.tensor (16 x 128 B box, 128-byte swizzle so the lanes' 16-byte reads
+//    are bank-conflict free), double buffered on two mbarriers per warp.  No lane computes a global address or holds
+//    prefetch registers, DRAM sees whole 128-byte lines, and warps never synchronise with each other inside the loop.
+//  * The layout epilogue (decoupled look-back over CTA tiles, copy of the pieces to their final place) is the one of
+//    k_rcs2_enc_fused.
+#pragma once
+#include <cuda.h>
+#include "static_v2.cuh"
+
+namespace trc {
+
+constexpr int      E3_RING_W  = 8;                      // ring words per lane (<= 3 left over + <= 4 new per 8-symbol block)
+constexpr uint32_t E3_RING_S  = 2048;                   // bytes between consecutive ring words of a lane (512 lanes x 4 B)
+constexpr uint32_t E3_RING_BYTES = E3_RING_W * E3_RING_S;
+constexpr uint32_t E3_TILE_BYTES = 16 * 128;            // one input stage of a warp: 16 calls x 128 bytes
+constexpr int      E3_STAGES = 2;
+
+// {cdf, freq} of every symbol as one 8-byte entry (one LDS.64 per symbol, nothing to unpack)
+struct __align__(16) EncTab2 { uint2 e[256]; };
+
+__global__ void k_build_enctab2(const cdf_t *__restrict__ cdf, unsigned cdfnum, EncTab2 *__restrict__ t,
+                                unsigned long long *__restrict__ lb_zero, unsigned lb_n) {
+    if (lb_zero) for (unsigned k = threadIdx.x; k < lb_n; k += blockDim.x) lb_zero[k] = 0;   // look-back words + tile counter
+    for (unsigned x = threadIdx.x; x < 256; x += blockDim.x) {
+        uint32_t c = 0, f = 0;
+        if (x < cdfnum) { c = cdf[x]; f = (uint32_t)cdf[x + 1] - c; }
+        t->e[x] = make_uint2(c, f);
+    }
+}
+
+// ---- the coder: range (64 bit) | low (64 bit) | pending word | carries out of the pending word ------------------------
+struct RcE96 {
+    uint32_t rl, rh, ll, lh, pend, rare;
+    uint32_t k;                                         // ring cursor: (words put so far mod 8) << 29
+    __device__ __forceinline__ void init() { rl = rh = 0xffffffffu; ll = lh = pend = rare = 0; k = 0; }
+    // one symbol (_rccdfenc_ + _rcenorm_, turborc_.h:215,105-109); ringlane = shared address of ring word 0 of this lane
+    __device__ __forceinline__ void encode(uint32_t c0, uint32_t f, uint32_t ringlane) {
+        asm volatile("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .u32 nl, nh, tl, th, a;\n\t"
+            ".reg .u64 nr, tt;\n\t"
+            "shf.r.wrap.b32 %0, %0, %1, 15;\n\t"         // range >>= 15
+            "shr.u32 %1, %1, 15;\n\t"
+            "mul.wide.u32 tt, %0, %7;\n\t"               // range * cdf[x]
+            "mov.b64 {tl, th}, tt;\n\t"
+            "mad.lo.u32 th, %1, %7, th;\n\t"
+            "add.cc.u32 %2, %2, tl;\n\t"                 // low += ...; the carry runs into the pending word
+            "addc.cc.u32 %3, %3, th;\n\t"
+            "addc.cc.u32 %4, %4, 0;\n\t"
+            "addc.u32 %5, %5, 0;\n\t"                    // ... and out of it (walk-back case)
+            "mul.wide.u32 nr, %0, %8;\n\t"               // range *= freq
+            "mov.b64 {nl, nh}, nr;\n\t"
+            "mad.lo.u32 nh, %1, %8, nh;\n\t"
+            "setp.eq.u32 p, nh, 0;\n\t"                  // range < 2^32: renormalise
+            "mad.hi.u32 a, %6, 16384, %9;\n\t"           // ring address = lane base + (k >> 29) * 2048
+            "@p st.shared.u32 [a], %4;\n\t"
+            "@p add.u32 %6, %6, 0x20000000;\n\t"
+            "@p mov.u32 %4, %3;\n\t"
+            "@p mov.u32 %3, %2;\n\t"
+            "@p mov.u32 %2, 0;\n\t"
+            "selp.u32 %1, nl, nh, p;\n\t"
+            "selp.u32 %0, 0, nl, p;\n\t"
+            "}"
+            : "+r"(rl), "+r"(rh), "+r"(ll), "+r"(lh), "+r"(pend), "+r"(rare), "+r"(k)
+            : "r"(c0), "r"(f), "r"(ringlane) : "memory");
+    }
+};
+
+// flush (rceflush turborc_.h:118-128) on the same state, words into the ring at sequence position `wr`
+__device__ __forceinline__ void e96_put(RcE96 &e, uint32_t w, uint32_t ringlane, uint32_t &wr) {
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(ringlane + (wr & (E3_RING_W - 1)) * E3_RING_S), "r"(e.pend) : "memory");
+    e.pend = w; wr++;
+}
+__device__ __forceinline__ void e96_add(RcE96 &e, uint32_t al, uint32_t ah) {
+    asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.u32 %3, %3, 0;"
+        : "+r"(e.ll), "+r"(e.lh), "+r"(e.pend), "+r"(e.rare) : "r"(al), "r"(ah));
+}
+
+// ---- TMA: 2-D tile of the input (tensor = [calls][chunk bytes], box = 16 calls x 128 bytes) ---------------------------
+__device__ __forceinline__ void tma_tile_2d(uint32_t smem_dst, const CUtensorMap *tmap, int x, int y, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(E3_TILE_BYTES) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_dst), "l"(tmap), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+// dynamic shared memory of k_rcs2_enc3: [pad to 1024][input tiles: warps x E3_STAGES x 2 KB][ring 16 KB]
+__host__ __device__ inline size_t e3_smem_bytes(unsigned nthreads, bool tma) {
+    return (tma ? 1024 + (size_t)(nthreads / 32) * E3_STAGES * E3_TILE_BYTES : 0) + E3_RING_BYTES;
+}
+
+// All calls handled here are FULL chunks (g.chunk bytes, a multiple of 16); a shorter last call of the batch is coded by
+// k_rcs2_enc_tail after this kernel.  n_calls counts the full calls only.
+template <bool TMA>
+__global__ void __launch_bounds__(LPC_MAX_NT, 2)
+k_rcs2_enc3(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ in, Geom g, size_t n_calls,
+            const EncTab2 *__restrict__ tab, uint8_t *__restrict__ slots, size_t slot_stride, unsigned calls_per_cta,
+            volatile unsigned long long *__restrict__ lb, uint64_t *__restrict__ out_off, uint8_t *__restrict__ out, unsigned flags) {
+    __shared__ __align__(16) uint2 ctab[256];
+    __shared__ uint64_t bar;
+    __shared__ uint64_t fullbar[(LPC_MAX_NT / 32) * E3_STAGES];
+    __shared__ uint32_t s_len[LPC_MAX_NT / 2], s_alen[LPC_MAX_NT / 2], s_blen[LPC_MAX_NT / 2], s_excl[LPC_MAX_NT / 2];
+    constexpr int NW = LPC_MAX_NT / 32;
+    __shared__ uint32_t s_wsum[NW + 1];
+    __shared__ unsigned long long s_base;
+    __shared__ unsigned s_tile;
+    extern __shared__ __align__(16) uint8_t dyn[];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t dyn0 = smem_u32(dyn);
+    const uint32_t tiles0 = TMA ? ((dyn0 + 1023u) & ~1023u) : dyn0;                       // 128-byte swizzle wants 1 KB aligned tiles
+    const uint32_t ring0 = TMA ? tiles0 + (blockDim.x >> 5) * E3_STAGES * E3_TILE_BYTES : dyn0;
+    if (threadIdx.x == 0) {
+        s_tile = (unsigned)atomicAdd((unsigned long long *)(lb + gridDim.x), 1ull);     // tile index in arrival order (look-back safe)
+        tma_fetch(ctab, tab->e, sizeof ctab, &bar);
+        if (TMA) {
+            for (unsigned k = 0; k < (blockDim.x >> 5) * E3_STAGES; k++)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&fullbar[k])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    const unsigned bid = s_tile;
+    const size_t j0 = (size_t)bid * calls_per_cta, j = j0 + (threadIdx.x >> 1);
+    const unsigned c = threadIdx.x & 1, r = threadIdx.x >> 1;
+    const bool live = j < n_calls && r < calls_per_cta;
+    const uint32_t n = (uint32_t)g.chunk;                                                  // every call here is a full chunk
+    const uint32_t nb = n >> 4;                                                            // 16-byte blocks per call (8 symbols per lane each)
+    const uint32_t fb0 = smem_u32(&fullbar[wid * E3_STAGES]);
+    const uint32_t mytiles = tiles0 + wid * E3_STAGES * E3_TILE_BYTES;
+    const int row0 = (int)(j0 + wid * 16);                                                 // first call (tensor row) of this warp
+    const uint32_t nst = (n + 127) >> 7;
+    if (TMA && lane == 0) {
+        tma_tile_2d(mytiles, &tmap, 0, row0, fb0);
+        if (nst > 1) tma_tile_2d(mytiles + E3_TILE_BYTES, &tmap, 128, row0, fb0 + 8);
+    }
+    tma_wait(&bar);
+    uint8_t *slot = slots + (live ? j : 0) * slot_stride;
+    const int64_t thr = rc_thr(n);
+    const uint32_t b1ref = n < 4 ? 4 : 4 + (uint32_t)((((size_t)n - 4) * 37) / 64);       // rccdf.c:126
+    const uint32_t b1 = (b1ref + 64 + 15) & ~15u;                                          // coder 1 lives at slot + b1 + 4 (word 0 of its image = scratch)
+    uint4 *gq = (uint4 *)(slot + (c ? b1 : 0));                                            // image of this coder in the slot: [scratch word][stream words ...]
+    const uint32_t ringlane = ring0 + threadIdx.x * 4;
+    const uint32_t tb = smem_u32(ctab);
+    // own half of OVERFLOWI (rccdf.c:46,133) as a word count: coder 1 fires when b1ref + 4 wr >= thr, coder 0 when 4 + 4 wr >= b1ref
+    const int64_t lim64 = c ? (thr - (int64_t)b1ref + 3) >> 2 : ((int64_t)b1ref - 4 + 3) >> 2;
+    const uint32_t limw = lim64 < 0 ? 0u : (uint32_t)lim64;
+    RcE96 e; e.init();
+    bool raw = n < 4 || !live;
+    uint32_t wr = 0, dr = 0;                                                               // words put / words drained to the slot
+    const uint8_t *ip = in + (live ? j : 0) * g.chunk;
+    const uint32_t lrow = lane >> 1;                                                       // row of this lane inside the warp tile
+    const uint32_t rowaddr = mytiles + lrow * 128, sw = (lrow & 7) << 4;
+    uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
+    if (!TMA && nb && !raw) { cur = ldg128(ip); nxt = nb > 1 ? ldg128(ip + 16) : cur; }
+#pragma unroll 1
+    for (uint32_t st = 0; st < nst; st++) {
+        if (TMA) mbar_wait(fb0 + (st & 1) * 8, (st >> 1) & 1);
+        const uint32_t cmax = min(8u, nb - st * 8);
+#pragma unroll 1
+        for (uint32_t cc = 0; cc < cmax; cc++) {
+            if (TMA) {
+                const uint32_t a = (rowaddr + (st & 1) * E3_TILE_BYTES) | ((cc << 4) ^ sw);
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(cur.x), "=r"(cur.y), "=r"(cur.z), "=r"(cur.w) : "r"(a));
+            }
+            const uint32_t b = st * 8 + cc;
+            uint4 nxt2 = nxt;
+            if (!TMA && b + 2 < nb && !raw) nxt2 = ldg128(ip + (size_t)(b + 2) * 16);
+            const uint32_t w[4] = { cur.x >> (8 * c), cur.y >> (8 * c), cur.z >> (8 * c), cur.w >> (8 * c) };
+            uint32_t tx[8], ty[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const uint32_t a = tb + (((q & 1) ? (w[q >> 1] >> 13) : (w[q >> 1] << 3)) & 0x7f8u);
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tx[q]), "=r"(ty[q]) : "r"(a));
+            }
+            const uint32_t k0 = e.k;
+#pragma unroll
+            for (int q = 0; q < 8; q++) e.encode(tx[q], ty[q], ringlane);
+            wr += (e.k - k0) >> 29;                                                        // <= 4 words per block
+            raw |= wr >= limw;                                                             // once per block: the tested quantity only grows
+            if (wr - dr >= 4) {                                                            // four finished words (ring image positions dr .. dr+3) leave as one 128-bit store
+                const uint32_t ra = ringlane + (dr & 4) * E3_RING_S;
+                uint4 v;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.x) : "r"(ra));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.y) : "r"(ra + E3_RING_S));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.z) : "r"(ra + 2 * E3_RING_S));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.w) : "r"(ra + 3 * E3_RING_S));
+                if (!raw) { gq[dr >> 2] = v; dr += 4; } else wr = dr + (wr & 3);           // a raw lane keeps coding but stops storing (its image is never read)
+            }
+            if (!TMA) { cur = nxt; nxt = nxt2; }
+        }
+        if (TMA) {
+            __syncwarp();
+            if (lane == 0 && st + 2 < nst) tma_tile_2d(mytiles + (st & 1) * E3_TILE_BYTES, &tmap, (int)(st + 2) * 128, row0, fb0 + (st & 1) * 8);
+        }
+    }
+    raw = __shfl_xor_sync(0xffffffffu, (int)raw, 1) || raw;                                // either half fired -> raw copy
+    if (!raw) {                                                                            // rceflush turborc_.h:118-128 (n is even: no odd tail)
+        if (e.rh == 0) { e96_put(e, e.lh, ringlane, wr); e.lh = e.ll; e.ll = 0; e.rh = e.rl; e.rl = 0; }
+        if (e.rh > 2u || (e.rh == 2u && e.rl != 0)) { e96_add(e, 0, 1); e96_put(e, e.lh, ringlane, wr); }   // range > 2^33
+        else { e96_add(e, 1, 0); e96_put(e, e.lh, ringlane, wr); e96_put(e, e.ll, ringlane, wr); }
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(ringlane + (wr & (E3_RING_W - 1)) * E3_RING_S), "r"(e.pend) : "memory");
+        // image positions dr .. wr are still in the ring (<= 3 + 3 + 1 words): two more 128-bit stores cover them
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t ra = ringlane + ((dr + 4 * h) & 4) * E3_RING_S;
+            uint4 v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.x) : "r"(ra));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.y) : "r"(ra + E3_RING_S));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.z) : "r"(ra + 2 * E3_RING_S));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.w) : "r"(ra + 3 * E3_RING_S));
+            if (dr + 4 * h <= wr) gq[(dr >> 2) + h] = v;
+        }
+    }
+    const uint32_t mypos = wr * 4, other = __shfl_xor_sync(0xffffffffu, mypos, 1);         // stream bytes of this coder / of its partner
+    const uint32_t rare = e.rare | __shfl_xor_sync(0xffffffffu, e.rare, 1);
+    if (c == 0 && r < LPC_MAX_NT / 2) {
+        UnitMeta m; m.a_off = 0; m.a_len = 0; m.b_off = b1 + 4; m.b_len = 0; m.len = 0; m.flags = 0;
+        if (live) {
+            const uint32_t p0 = mypos, p1 = other;
+            if (!raw && (int64_t)(4 + p0 + p1) >= thr) raw = true;                         // rccdf.c:142
+            if ((rare || (flags & 1u)) && !raw) {                                          // wrapped pending word (flags & 1: test hook): walk-back coder
+                __shared__ uint32_t s_ctab32[256];
+                // (only this lane needs the 32-bit table; built on the fly from the 8-byte entries)
+                for (int x = 0; x < 256; x++) s_ctab32[x] = ctab[x].x | ctab[x].y << 16;
+                rc_static_enc_call<2, true>(ip, n, s_ctab32, nullptr, slot, m);
+                if (!(m.flags & UM_RAW)) {                                                 // move stream 1 to where the epilogue expects it
+                    for (uint32_t k2 = m.b_len; k2 > 0; k2 -= 4) *(uint32_t *)(slot + b1 + 4 + k2 - 4) = *(uint32_t *)(slot + m.b_off + k2 - 4);
+                    m.b_off = b1 + 4;
+                }
+            } else { m.a_len = raw ? 0 : 4 + p0; m.b_len = raw ? 0 : p1; m.len = raw ? n : 4 + p0 + p1; m.flags = raw ? UM_RAW : 0; }
+        }
+        s_len[r] = m.len; s_alen[r] = (m.flags & UM_RAW) ? 0xffffffffu : m.a_len; s_blen[r] = m.b_len;
+    }
+    __syncthreads();
+    // ---- exclusive scan of the call lengths of this CTA (calls_per_cta <= 256: thread t scans entry t)
+    uint32_t v = threadIdx.x < calls_per_cta ? s_len[threadIdx.x] : 0, inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += t; }
+    if (lane == 31) s_wsum[wid] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (unsigned k = 0; k < (blockDim.x + 31) / 32; k++) { const uint32_t t = s_wsum[k]; s_wsum[k] = run; run += t; }
+        s_wsum[NW] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x < calls_per_cta) s_excl[threadIdx.x] = s_wsum[wid] + inc - v;
+    // ---- decoupled look-back for the CTA's base offset
+    if (wid == 0) {
+        const unsigned long long agg = s_wsum[NW];
+        if (lane == 0) { lb[bid] = (bid == 0 ? LB_INC : LB_AGG) | agg; __threadfence(); }
+        unsigned long long base = 0;
+        if (bid) {
+            long long idx = (long long)bid - 1;
+            for (;;) {
+                const long long k = idx - lane;
+                unsigned long long st = LB_INC;                   // before CTA 0: inclusive prefix 0
+                if (k >= 0) do { st = lb[k]; } while ((st >> 62) == 0);
+                const unsigned incl = __ballot_sync(0xffffffffu, (st >> 62) == 2);
+                const unsigned first = incl ? __ffs((int)incl) - 1 : 32;
+                unsigned long long val = lane <= first ? (st & LB_VAL) : 0;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                base += val;
+                if (incl) break;
+                idx -= 32;
+            }
+            if (lane == 0) { lb[bid] = LB_INC | (base + agg); __threadfence(); }
+        }
+        if (lane == 0) s_base = base;
+    }
+    __syncthreads();
+    const unsigned long long base = s_base;
+    if (threadIdx.x < calls_per_cta && j0 + threadIdx.x < n_calls) out_off[j0 + threadIdx.x] = base + s_excl[threadIdx.x];
+    if (threadIdx.x == 0 && j0 + calls_per_cta >= n_calls) out_off[n_calls] = base + s_wsum[NW];
+    // ---- layout: a warp per call, pieces from the slot (or the input, for a raw call) to their final place
+    for (unsigned q = wid; q < calls_per_cta && j0 + q < n_calls; q += blockDim.x >> 5) {
+        uint8_t *dst = out + base + s_excl[q];
+        uint8_t *sl = slots + (j0 + q) * slot_stride;
+        if (s_alen[q] == 0xffffffffu) { group_copy4(dst, in + (j0 + q) * g.chunk, n, lane, 32); continue; }
+        if (lane == 0) *(uint32_t *)sl = s_alen[q] - 4;                                    // len0 header (rccdf.c:141) over the scratch word
+        __syncwarp();
+        if (((uintptr_t)dst & 3) == 0) {
+            const uint32_t *pa = (const uint32_t *)sl, *pb = (const uint32_t *)(sl + b1 + 4);
+            const uint32_t wa = s_alen[q] >> 2, W = wa + (s_blen[q] >> 2);
+            uint32_t *d = (uint32_t *)dst;
+            for (uint32_t w0 = 0; w0 < W; w0 += LB_U * 32) {
+                uint32_t vv[LB_U];
+#pragma unroll
+                for (int k = 0; k < LB_U; k++) { const uint32_t w = w0 + k * 32 + lane; vv[k] = w < wa ? pa[w] : (w < W ? pb[w - wa] : 0u); }
+#pragma unroll
+                for (int k = 0; k < LB_U; k++) { const uint32_t w = w0 + k * 32 + lane; if (w < W) d[w] = vv[k]; }
+            }
+        } else { group_copy(dst, sl, s_alen[q], lane, 32); if (s_blen[q]) group_copy(dst + s_alen[q], sl + b1 + 4, s_blen[q], lane, 32); }
+    }
+}
+
+// The last call of a batch when it is shorter than a chunk: one warp, generic coder (any length, walk-back carry), placed
+// behind the full calls.  Runs after k_rcs2_enc3 on the same stream (out_off[n_full] is the running total it left).
+__global__ void k_rcs2_enc_tail(const uint8_t *__restrict__ in, Geom g, size_t n_full, const EncTab2 *__restrict__ tab,
+                                uint8_t *__restrict__ slots, size_t slot_stride, uint64_t *__restrict__ out_off, uint8_t *__restrict__ out) {
+    __shared__ uint32_t ctab[256];
+    __shared__ UnitMeta sm;
+    for (unsigned x = threadIdx.x; x < 256; x += blockDim.x) ctab[x] = tab->e[x].x | tab->e[x].y << 16;
+    __syncwarp();
+    size_t start, n; call_span(g, n_full, start, n);
+    uint8_t *slot = slots + n_full * slot_stride;
+    if (threadIdx.x == 0) { UnitMeta m; rc_static_enc_call<2, true>(in + start, n, ctab, nullptr, slot, m); sm = m; }
+    __syncwarp();
+    const UnitMeta m = sm;
+    const uint64_t o = n_full ? out_off[n_full] : 0;
+    if (n_full == 0 && threadIdx.x == 0) out_off[0] = 0;
+    uint8_t *dst = out + o;
+    if (m.flags & UM_RAW) group_copy(dst, in + start, n, threadIdx.x, 32);
+    else { group_copy(dst, slot, m.a_len, threadIdx.x, 32); if (m.b_len) group_copy(dst + m.a_len, slot + m.b_off, m.b_len, threadIdx.x, 32); }
+    if (threadIdx.x == 0) out_off[n_full + 1] = o + m.len;
+}
+
+}  // namespace trc

@@ -6,6 +6,7 @@
 #include "rc_static.cuh"
 #include "adaptive.cuh"
 #include "static_v2.cuh"
+#include "rcs2_v3.cuh"
 #include "adaptive_coop.cuh"
 #include "adaptive_v3.cuh"
 #include "vnibble.cuh"
@@ -44,6 +45,30 @@ static void prof_mark(cudaStream_t st) {
     if (g_prof_n < 8) cudaEventRecord(g_pev[g_prof_n++], st);
 }
 
+// ---- per-device one-time state (several devices may be driven from one process) -----------------------------------
+constexpr int MAX_DEV = 64;
+static int cur_dev() { int d = 0; cudaGetDevice(&d); return d < 0 || d >= MAX_DEV ? 0 : d; }
+static int sm_count() {
+    static int n_sm[MAX_DEV];
+    const int d = cur_dev();
+    if (!n_sm[d]) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); n_sm[d] = n > 0 ? n : 148; }
+    return n_sm[d];
+}
+// TRC_RCS2 encoder input staging: 1 = TMA 2-D tiles (default), 0 = per-lane 128-bit loads (A/B runs)
+static const int g_enc_tma = getenv("TRC_ENC_TMA") ? atoi(getenv("TRC_ENC_TMA")) : 1;
+typedef CUresult (*tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encode() {
+    static tmap_encode_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (tmap_encode_fn)p;
+    }
+    return fn;
+}
+
+static int dev_attrs();
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 static inline size_t al16(size_t x) { return (x + 15) & ~(size_t)15; }
 
@@ -58,8 +83,7 @@ static inline size_t n_tables(size_t n_calls, size_t cpc) { return cpc ? (n_call
 // the throughput kernels (static_v2.cuh) need 16-byte aligned calls and table groups that do not split a CTA
 // lane-per-coder launch shape: (calls per CTA, CTAs).  Batches that fit one wave get one equally loaded CTA per SM.
 static void lpc_shape(size_t n_calls, size_t cpc, unsigned &calls_per_cta, unsigned &ctas) {
-    static int n_sm = 0;
-    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+    const int n_sm = sm_count();
     calls_per_cta = LPC_NT / 2;
     const size_t per_sm = (n_calls + n_sm - 1) / n_sm;
     // one wave of equally loaded CTAs: k CTAs per SM (k <= 3 keeps registers and the 33 KB tables of each CTA resident)
@@ -111,10 +135,15 @@ static int make_plan(int codec, size_t total_len, size_t chunk_len, Plan &p) {
     return TRC_OK;
 }
 
-static int sm_count() {
-    static int n_sm = 0;
-    if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
-    return n_sm;
+// kernels that need more than 48 KB of dynamic shared memory: the opt-in is per device
+static int dev_attrs() {
+    static bool done[MAX_DEV];
+    const int d = cur_dev();
+    if (done[d]) return TRC_OK;
+    CK(cudaFuncSetAttribute(k_rcs2_enc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem_bytes(LPC_MAX_NT, true)));
+    CK(cudaFuncSetAttribute(k_rcs2_enc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem_bytes(LPC_MAX_NT, false)));
+    done[d] = true;
+    return TRC_OK;
 }
 
 // adaptive byte rANS encoder, third generation: model pass (one warp per unit) then coding pass (one lane per state)
@@ -216,19 +245,41 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     if (codec == ANSW && !(((uintptr_t)d_in & 3) == 0 && (chunks_per_cdf == 0 || chunks_per_cdf % V2_NT == 0))) return TRC_E_ARG;
     TableSet *tabs = (TableSet *)(sc + p.off_tabs);
     const bool fused = g_fused && codec == RCS2 && v2 && chunks_per_cdf == 0;
-    unsigned f_cpcta = 0, f_ctas = 0;
-    if (fused) lpc_shape(g.n_calls, 0, f_cpcta, f_ctas);
-    if (v2 || codec == ANSW) {   // symbol tables once per launch (+ the look-back words of the fused encoder)
-        k_build_tables<<<dim3((unsigned)n_tables(g.n_calls, chunks_per_cdf), 1), 256, 0, st>>>(d_cdf, cdfnum, tabs, 0,
-            fused ? (unsigned long long *)(sc + p.off_lb) : nullptr, f_ctas + 1);
+    if (fused) {                 // TRC_RCS2, one table: coder + offsets + layout in ONE kernel (rcs2_v3.cuh)
+        const size_t n_full = total_len / chunk_len;                        // full chunks; a shorter last call goes to the tail kernel
+        const bool tail = total_len % chunk_len != 0;
+        EncTab2 *t2 = (EncTab2 *)tabs;
+        unsigned cpcta = 0, ctas = 0;
+        if (n_full) lpc_shape(n_full, 0, cpcta, ctas);
+        k_build_enctab2<<<1, 256, 0, st>>>(d_cdf, cdfnum, t2, (unsigned long long *)(sc + p.off_lb), ctas + 1);
         CK_LAUNCH();
-    }
-    if (fused) {                 // coder + offsets + layout in ONE kernel
         prof_mark(st);
-        k_rcs2_enc_fused<<<f_ctas, (2 * f_cpcta + 31) & ~31u, 0, st>>>(d_in, g, g.n_calls, tabs, slots, p.slot_stride, f_cpcta,
-            (volatile unsigned long long *)(sc + p.off_lb), d_out_off, d_out);
-        CK_LAUNCH(); prof_mark(st); prof_mark(st); prof_mark(st);
+        if (n_full) {
+            const unsigned nt = (2 * cpcta + 31) & ~31u;
+            const bool tma = g_enc_tma && tmap_encode() && n_full < (1ull << 31);
+            CUtensorMap tm; memset(&tm, 0, sizeof tm);
+            if (tma) {                                                      // input as a 2-D tensor [calls][chunk bytes], box = 16 calls x 128 bytes
+                const cuuint64_t dims[2] = { (cuuint64_t)chunk_len, (cuuint64_t)n_full }, strides[1] = { (cuuint64_t)chunk_len };
+                const cuuint32_t box[2] = { 128, 16 }, estr[2] = { 1, 1 };
+                CUresult r = tmap_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)d_in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled failed (%d)", (int)r); return TRC_E_CUDA; }
+            }
+            const size_t smem = e3_smem_bytes(nt, tma);
+            rc = dev_attrs(); if (rc) return rc;
+            if (tma) k_rcs2_enc3<true><<<ctas, nt, smem, st>>>(tm, d_in, g, n_full, t2, slots, p.slot_stride, cpcta,
+                                                              (volatile unsigned long long *)(sc + p.off_lb), d_out_off, d_out, g_force_redo ? 1u : 0u);
+            else     k_rcs2_enc3<false><<<ctas, nt, smem, st>>>(tm, d_in, g, n_full, t2, slots, p.slot_stride, cpcta,
+                                                               (volatile unsigned long long *)(sc + p.off_lb), d_out_off, d_out, g_force_redo ? 1u : 0u);
+            CK_LAUNCH();
+        }
+        if (tail) { k_rcs2_enc_tail<<<1, 32, 0, st>>>(d_in, g, n_full, t2, slots, p.slot_stride, d_out_off, d_out); CK_LAUNCH(); }
+        prof_mark(st); prof_mark(st); prof_mark(st);
         return TRC_OK;
+    }
+    if (v2 || codec == ANSW) {   // symbol tables once per launch
+        k_build_tables<<<dim3((unsigned)n_tables(g.n_calls, chunks_per_cdf), 1), 256, 0, st>>>(d_cdf, cdfnum, tabs, 0);
+        CK_LAUNCH();
     }
     const unsigned v2nt = v2_shape(g.n_calls, chunks_per_cdf);
     prof_mark(st);
