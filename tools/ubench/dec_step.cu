@@ -98,6 +98,37 @@ struct D2 {
     }
 };
 
+// ---- variant 3: 64-bit conversions (one XU op each), magic constant folded into the FFMA, one unsigned test, {cdf,freq} 8-byte
+//      entries, one-word look-ahead, ring cursor in the top bits of a register (wraps for free, address = one shift-and-add)
+struct D3 {
+    uint32_t rl, rh, cl, ch, n0, k; bool bad;
+    const uint8_t *lut; const uint2 *dtab2; uint32_t ringlane;      // ringlane: shared address of ring word 0 of this lane; stride 2048 B
+    __device__ __forceinline__ void step(uint32_t &x_out) {
+        rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;
+        const float qf = fmaf(__ull2float_rz((uint64_t)ch << 32 | cl), rcp_approx(__ull2float_rn((uint64_t)rh << 32 | rl)), 12582911.5f);
+        const uint32_t x = lut[__float_as_uint(qf) & 0x7fffu];
+        const uint2 e = dtab2[x];
+        const uint64_t rp = (uint64_t)rl * e.x, fr = (uint64_t)rl * e.y;
+        const uint32_t pl = (uint32_t)rp, ph = (uint32_t)(rp >> 32) + rh * e.x;
+        const uint32_t fl = (uint32_t)fr, fh = (uint32_t)(fr >> 32) + rh * e.y;
+        uint32_t dl, dh;
+        asm("sub.cc.u32 %0, %2, %4;\n\tsubc.u32 %1, %3, %5;" : "=r"(dl), "=r"(dh) : "r"(cl), "r"(ch), "r"(pl), "r"(ph));
+        bad |= ((uint64_t)dh << 32 | dl) >= ((uint64_t)fh << 32 | fl);
+        uint32_t a;
+        asm("mad.hi.u32 %0, %1, 32768, %2;" : "=r"(a) : "r"(k), "r"(ringlane));     // (k >> 28) * 2048 + lane base
+        asm volatile("{\n\t.reg .pred p;\n\t"
+            "setp.eq.u32 p, %7, 0;\n\t"
+            "selp.u32 %0, %6, %7, p;\n\t"       // rh = p ? fl : fh
+            "selp.u32 %1, 0, %6, p;\n\t"        // rl = p ? 0 : fl
+            "selp.u32 %2, %8, %9, p;\n\t"       // ch = p ? dl : dh
+            "selp.u32 %3, %4, %8, p;\n\t"       // cl = p ? n0 : dl
+            "@p ld.shared.u32 %4, [%10];\n\t"
+            "@p add.u32 %5, %5, 0x10000000;\n\t"
+            "}" : "=r"(rh), "=r"(rl), "=r"(ch), "=r"(cl), "+r"(n0), "+r"(k) : "r"(fl), "r"(fh), "r"(dl), "r"(dh), "r"(a) : "memory");
+        x_out = x;
+    }
+};
+
 template <int V>
 __global__ void __launch_bounds__(T, 2) k(const uint4 *__restrict__ in, const uint32_t *__restrict__ gdtab, const uint8_t *__restrict__ glut,
                                           uint2 *__restrict__ out, uint32_t *__restrict__ flags, int nblk) {
@@ -112,7 +143,7 @@ __global__ void __launch_bounds__(T, 2) k(const uint4 *__restrict__ in, const ui
     const size_t gid = (size_t)blockIdx.x * T + threadIdx.x;
     const uint4 *ip = in + gid * (size_t)(nblk + 4);                // private word stream (4 words per block on average is plenty)
     uint32_t *ring = ringbuf + threadIdx.x;
-    constexpr uint32_t RS = V == 0 ? T : 512;                       // lane stride in words
+    constexpr uint32_t RS = V == 0 ? T : 512;                       // lane stride in words (512: a power of two, see D1/D3)                       // lane stride in words
     auto ring_put = [&](uint32_t w, const uint4 &v) {
         ring[((w + 0) & (RING_W - 1)) * RS] = v.x; ring[((w + 1) & (RING_W - 1)) * RS] = v.y;
         ring[((w + 2) & (RING_W - 1)) * RS] = v.z; ring[((w + 3) & (RING_W - 1)) * RS] = v.w;
@@ -136,6 +167,25 @@ __global__ void __launch_bounds__(T, 2) k(const uint4 *__restrict__ in, const ui
             for (int s = 0; s < 4; s++) { d.step(x); a1 |= x << (8 * s); }
             if (need) { ring_put(fi, t4); fi += 4; qi++; }
             acc += d.bad; d.bad = 0;
+            op[b] = make_uint2(a0, a1);
+        }
+    } else if (V == 3) {
+        D3 d; d.lut = lut; d.dtab2 = dtab2; d.ringlane = (uint32_t)__cvta_generic_to_shared(ring);
+        d.rl = d.rh = 0xffffffffu; d.ch = ring[0] >> 1; d.cl = ring[RS]; d.n0 = ring[2 * RS]; d.bad = false; d.k = 3u << 28;
+        uint32_t ci = 3, k_prev = d.k;
+#pragma unroll 1
+        for (int b = 0; b < nblk; b++) {
+            const bool need = fi - ci <= 10;
+            uint4 t4 = make_uint4(0, 0, 0, 0);
+            if (need) t4 = ip[qi];
+            uint32_t a0 = 0, a1 = 0, x;
+#pragma unroll
+            for (int s = 0; s < 4; s++) { d.step(x); a0 |= x << (8 * s); }
+#pragma unroll
+            for (int s = 0; s < 4; s++) { d.step(x); a1 |= x << (8 * s); }
+            ci += (d.k - k_prev) >> 28; k_prev = d.k;
+            if (need) { ring_put(fi, t4); fi += 4; qi++; }
+            acc += d.bad ? 1u : 0u; d.bad = false;
             op[b] = make_uint2(a0, a1);
         }
     } else {
@@ -207,6 +257,7 @@ int main(int argc, char **argv) {
     printf("lanes %zu, %d symbols per lane, %d CTAs x %d\n", lanes, nblk * 8, ctas, T);
     run<0>("d0 round-1 step", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
     run<1>("d1 32-bit cvt, single test, 2-word la", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<3>("d3 64-bit cvt, folded magic, top-bit cursor", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
     run<2>("d2 same, 1-word look-ahead", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
     return 0;
 }

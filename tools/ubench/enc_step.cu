@@ -172,6 +172,86 @@ struct V4 {
     __device__ __forceinline__ void blockend(uint32_t) {}
 };
 
+// ---- variant 5: variant 1 with shifts and state moves forced onto the fma pipe (multiplier / one in registers ptxas cannot fold)
+__device__ uint32_t g_M, g_ONE;
+struct V5 {
+    uint32_t rl, rh, ll, lh, pend, rare, sa, M, ONE;
+    __device__ __forceinline__ void init(uint32_t *, uint32_t sa0) { rl = rh = 0xffffffffu; ll = lh = pend = rare = 0; sa = sa0; M = g_M; ONE = g_ONE; }
+    __device__ __forceinline__ void step(uint32_t c0, uint32_t f) {
+        asm volatile("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .u32 nl, nh, tl, th, t, z;\n\t"
+            ".reg .u64 nr, tt, rr;\n\t"
+            "mul.hi.u32 t, %0, %10;\n\t"
+            "mov.u32 z, 0;\n\t"
+            "mov.b64 rr, {t, z};\n\t"
+            "mad.wide.u32 rr, %1, %10, rr;\n\t"
+            "mov.b64 {%0, %1}, rr;\n\t"
+            "mul.wide.u32 tt, %0, %7;\n\t"
+            "mov.b64 {tl, th}, tt;\n\t"
+            "mad.lo.u32 th, %1, %7, th;\n\t"
+            "add.cc.u32 %2, %2, tl;\n\t"
+            "addc.cc.u32 %3, %3, th;\n\t"
+            "addc.cc.u32 %4, %4, 0;\n\t"
+            "addc.u32 %5, %5, 0;\n\t"
+            "mul.wide.u32 nr, %0, %8;\n\t"
+            "mov.b64 {nl, nh}, nr;\n\t"
+            "mad.lo.u32 nh, %1, %8, nh;\n\t"
+            "setp.eq.u32 p, nh, 0;\n\t"
+            "@p st.shared.u32 [%6], %4;\n\t"
+            "@p add.u32 %6, %6, %9;\n\t"
+            "@p mul.lo.u32 %4, %3, %11;\n\t"
+            "@p mul.lo.u32 %3, %2, %11;\n\t"
+            "@p mov.u32 %2, 0;\n\t"
+            "selp.u32 %1, nl, nh, p;\n\t"
+            "selp.u32 %0, 0, nl, p;\n\t"
+            "}"
+            : "+r"(rl), "+r"(rh), "+r"(ll), "+r"(lh), "+r"(pend), "+r"(rare), "+r"(sa)
+            : "r"(c0), "r"(f), "n"(T * 4), "r"(M), "r"(ONE) : "memory");
+    }
+    __device__ __forceinline__ uint32_t fin() { return rare + pend + sa; }
+    __device__ __forceinline__ void blockend(uint32_t sa0) { sa = sa0; }
+};
+// ---- variant 6: variant 5 but only the shifts on the fma pipe
+struct V6 {
+    uint32_t rl, rh, ll, lh, pend, rare, sa, M;
+    __device__ __forceinline__ void init(uint32_t *, uint32_t sa0) { rl = rh = 0xffffffffu; ll = lh = pend = rare = 0; sa = sa0; M = g_M; }
+    __device__ __forceinline__ void step(uint32_t c0, uint32_t f) {
+        asm volatile("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .u32 nl, nh, tl, th, t, z;\n\t"
+            ".reg .u64 nr, tt, rr;\n\t"
+            "mul.hi.u32 t, %0, %10;\n\t"
+            "mov.u32 z, 0;\n\t"
+            "mov.b64 rr, {t, z};\n\t"
+            "mad.wide.u32 rr, %1, %10, rr;\n\t"
+            "mov.b64 {%0, %1}, rr;\n\t"
+            "mul.wide.u32 tt, %0, %7;\n\t"
+            "mov.b64 {tl, th}, tt;\n\t"
+            "mad.lo.u32 th, %1, %7, th;\n\t"
+            "add.cc.u32 %2, %2, tl;\n\t"
+            "addc.cc.u32 %3, %3, th;\n\t"
+            "addc.cc.u32 %4, %4, 0;\n\t"
+            "addc.u32 %5, %5, 0;\n\t"
+            "mul.wide.u32 nr, %0, %8;\n\t"
+            "mov.b64 {nl, nh}, nr;\n\t"
+            "mad.lo.u32 nh, %1, %8, nh;\n\t"
+            "setp.eq.u32 p, nh, 0;\n\t"
+            "@p st.shared.u32 [%6], %4;\n\t"
+            "@p add.u32 %6, %6, %9;\n\t"
+            "@p mov.u32 %4, %3;\n\t"
+            "@p mov.u32 %3, %2;\n\t"
+            "@p mov.u32 %2, 0;\n\t"
+            "selp.u32 %1, nl, nh, p;\n\t"
+            "selp.u32 %0, 0, nl, p;\n\t"
+            "}"
+            : "+r"(rl), "+r"(rh), "+r"(ll), "+r"(lh), "+r"(pend), "+r"(rare), "+r"(sa)
+            : "r"(c0), "r"(f), "n"(T * 4), "r"(M) : "memory");
+    }
+    __device__ __forceinline__ uint32_t fin() { return rare + pend + sa; }
+    __device__ __forceinline__ void blockend(uint32_t sa0) { sa = sa0; }
+};
+
 template <class V, int CTAS_PER_SM>
 __global__ void __launch_bounds__(T, CTAS_PER_SM) k(const uint4 *__restrict__ in, const uint2 *__restrict__ gtab, uint32_t *__restrict__ slots, uint32_t *__restrict__ out, int nblk) {
     __shared__ uint2 tab[256];
@@ -237,11 +317,14 @@ int main(int argc, char **argv) {
     cudaMalloc(&d_in, h.size()); cudaMemcpy(d_in, h.data(), h.size(), cudaMemcpyHostToDevice);
     cudaMalloc(&d_tab, 2048); cudaMemcpy(d_tab, tab.data(), 2048, cudaMemcpyHostToDevice);
     cudaMalloc(&d_slots, lanes * (size_t)(nblk * 8 + 16) * 4); cudaMalloc(&d_out, lanes * 4);
+    { uint32_t m = 0x20000, one = 1; cudaMemcpyToSymbol(g_M, &m, 4); cudaMemcpyToSymbol(g_ONE, &one, 4); }
     printf("lanes %zu, %d symbols per lane, %d CTAs x %d\n", lanes, nblk * 8, ctas, T);
     run<V0, 2>("v0 round-1 step, global slot", d_in, d_tab, d_slots, d_out, nblk, ctas);
     run<V1, 2>("v1 96-bit low, smem ring", d_in, d_tab, d_slots, d_out, nblk, ctas);
     run<V2, 2>("v2 mad64 + ilh (C)", d_in, d_tab, d_slots, d_out, nblk, ctas);
     run<V3, 2>("v3 mad64 + ilh (asm)", d_in, d_tab, d_slots, d_out, nblk, ctas);
+    run<V5, 2>("v5 v1 + shifts/moves on fma pipe", d_in, d_tab, d_slots, d_out, nblk, ctas);
+    run<V6, 2>("v6 v1 + shifts on fma pipe", d_in, d_tab, d_slots, d_out, nblk, ctas);
     run<V4, 2>("v4 96-bit low, global slot", d_in, d_tab, d_slots, d_out, nblk, ctas);
     run<V4, 3>("v4, 3 CTAs per SM", d_in, d_tab, d_slots, d_out, nblk, ctas * 3 / 2);
     run<V1, 3>("v1, 3 CTAs per SM", d_in, d_tab, d_slots, d_out, nblk, ctas * 3 / 2);

@@ -9,9 +9,10 @@
 //    and leave as 128-bit stores, four words at a time.
 //  * The coder step keeps `low` as a 96-bit number whose top word is the pending output word, so the carry of
 //    low += range * cdf[x] (turborc_.h:215, _rccarry_ :103) runs straight into the pending word through the add-with-carry
-//    chain: no carry flag, no compare, no select -- 22.5 SASS instructions per symbol instead of 41.  A carry OUT of the
-//    pending word (it held 0xffffffff: the reference would walk back through stored words, p ~ 2^-32 per word) lands in a
-//    fourth chain word; a lane that ever sees one has its call redone by the exact walk-back coder.
+//    chain: no carry flag, no compare, no select -- 21.5 SASS instructions per symbol instead of 41.  A carry OUT of the
+//    pending word (it held 0xffffffff: the reference would walk back through stored words, p ~ 2^-32 per word) leaves a
+//    ZERO word behind; every stored word passes through a running minimum, and a call that ever stored a zero word
+//    (wrapped or genuine, both p ~ 2^-32 per word) is redone by the exact walk-back coder.
 //  * INPUT arrives by TMA: the batch is described as a 2-D tensor [calls][chunk bytes] and every warp pulls the next
 //    128 bytes of its 16 calls with ONE cp.async.bulk.tensor (16 x 128 B box, 128-byte swizzle so the lanes' 16-byte reads
 //    are bank-conflict free), double buffered on two mbarriers per warp.  No lane computes a global address or holds
@@ -24,9 +25,11 @@
 
 namespace trc {
 
+constexpr int      E3_MAX_NT  = 768;                    // one CTA per SM: 384 calls, 24 warps
 constexpr int      E3_RING_W  = 8;                      // ring words per lane (<= 3 left over + <= 4 new per 8-symbol block)
-constexpr uint32_t E3_RING_S  = 2048;                   // bytes between consecutive ring words of a lane (512 lanes x 4 B)
-constexpr uint32_t E3_RING_BYTES = E3_RING_W * E3_RING_S;
+constexpr uint32_t E3_RING_S  = 4096;                   // bytes between consecutive ring words of a lane (room for 1024 lanes; a power of two so that the
+                                                        // ring address is ONE shift-and-add of the cursor)
+constexpr uint32_t E3_LEAD    = 6;                      // blocks a warp may run ahead of the slowest warp of its CTA (see the pacing note in k_rcs2_enc3)
 constexpr uint32_t E3_TILE_BYTES = 16 * 128;            // one input stage of a warp: 16 calls x 128 bytes
 constexpr int      E3_STAGES = 2;
 
@@ -45,9 +48,12 @@ __global__ void k_build_enctab2(const cdf_t *__restrict__ cdf, unsigned cdfnum, 
 
 // ---- the coder: range (64 bit) | low (64 bit) | pending word | carries out of the pending word ------------------------
 struct RcE96 {
-    uint32_t rl, rh, ll, lh, pend, rare;
+    uint32_t rl, rh, ll, lh, pend;
+    uint32_t nz;                                        // min over every word stored so far: 0 = some stored word was zero (see below)
     uint32_t k;                                         // ring cursor: (words put so far mod 8) << 29
-    __device__ __forceinline__ void init() { rl = rh = 0xffffffffu; ll = lh = pend = rare = 0; k = 0; }
+    // pend starts at 1: the first renormalisation stores it as a scratch word in front of the stream (never part of the output),
+    // no carry can reach it before that (low + range < 2^64 until the first renormalisation), and it must not look like a zero word
+    __device__ __forceinline__ void init() { rl = rh = 0xffffffffu; ll = lh = 0; pend = 1; nz = 1; k = 0; }
     // one symbol (_rccdfenc_ + _rcenorm_, turborc_.h:215,105-109); ringlane = shared address of ring word 0 of this lane
     __device__ __forceinline__ void encode(uint32_t c0, uint32_t f, uint32_t ringlane) {
         asm volatile("{\n\t"
@@ -61,13 +67,12 @@ struct RcE96 {
             "mad.lo.u32 th, %1, %7, th;\n\t"
             "add.cc.u32 %2, %2, tl;\n\t"                 // low += ...; the carry runs into the pending word
             "addc.cc.u32 %3, %3, th;\n\t"
-            "addc.cc.u32 %4, %4, 0;\n\t"
-            "addc.u32 %5, %5, 0;\n\t"                    // ... and out of it (walk-back case)
+            "addc.u32 %4, %4, 0;\n\t"
             "mul.wide.u32 nr, %0, %8;\n\t"               // range *= freq
             "mov.b64 {nl, nh}, nr;\n\t"
             "mad.lo.u32 nh, %1, %8, nh;\n\t"
             "setp.eq.u32 p, nh, 0;\n\t"                  // range < 2^32: renormalise
-            "mad.hi.u32 a, %6, 16384, %9;\n\t"           // ring address = lane base + (k >> 29) * 2048
+            "mad.hi.u32 a, %6, 32768, %9;\n\t"           // ring address = lane base + (k >> 29) * 4096
             "@p st.shared.u32 [a], %4;\n\t"
             "@p add.u32 %6, %6, 0x20000000;\n\t"
             "@p mov.u32 %4, %3;\n\t"
@@ -76,7 +81,7 @@ struct RcE96 {
             "selp.u32 %1, nl, nh, p;\n\t"
             "selp.u32 %0, 0, nl, p;\n\t"
             "}"
-            : "+r"(rl), "+r"(rh), "+r"(ll), "+r"(lh), "+r"(pend), "+r"(rare), "+r"(k)
+            : "+r"(rl), "+r"(rh), "+r"(ll), "+r"(lh), "+r"(pend), "+r"(nz), "+r"(k)
             : "r"(c0), "r"(f), "r"(ringlane) : "memory");
     }
 };
@@ -84,18 +89,23 @@ struct RcE96 {
 // flush (rceflush turborc_.h:118-128) on the same state, words into the ring at sequence position `wr`
 __device__ __forceinline__ void e96_put(RcE96 &e, uint32_t w, uint32_t ringlane, uint32_t &wr) {
     asm volatile("st.shared.u32 [%0], %1;" :: "r"(ringlane + (wr & (E3_RING_W - 1)) * E3_RING_S), "r"(e.pend) : "memory");
+    e.nz = min(e.nz, e.pend);
     e.pend = w; wr++;
 }
 __device__ __forceinline__ void e96_add(RcE96 &e, uint32_t al, uint32_t ah) {
-    asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.u32 %3, %3, 0;"
-        : "+r"(e.ll), "+r"(e.lh), "+r"(e.pend), "+r"(e.rare) : "r"(al), "r"(ah));
+    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+        : "+r"(e.ll), "+r"(e.lh), "+r"(e.pend) : "r"(al), "r"(ah));
 }
 
 // ---- TMA: 2-D tile of the input (tensor = [calls][chunk bytes], box = 16 calls x 128 bytes) ---------------------------
+// The input is read exactly once: its lines are marked evict-first in L2 so that the slot images written by this kernel
+// (read back by its layout epilogue) stay resident instead of being pushed out to DRAM by the input stream.
 __device__ __forceinline__ void tma_tile_2d(uint32_t smem_dst, const CUtensorMap *tmap, int x, int y, uint32_t bar) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(E3_TILE_BYTES) : "memory");
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_dst), "l"(tmap), "r"(x), "r"(y), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(smem_dst), "l"(tmap), "r"(x), "r"(y), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
@@ -104,34 +114,44 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
 }
 
-// dynamic shared memory of k_rcs2_enc3: [pad to 1024][input tiles: warps x E3_STAGES x 2 KB][ring 16 KB]
+// dynamic shared memory of k_rcs2_enc3: [pad to 2048][table 2 KB][input tiles: warps x E3_STAGES x 2 KB][ring: 8 words x 4 KB]
 __host__ __device__ inline size_t e3_smem_bytes(unsigned nthreads, bool tma) {
-    return (tma ? 1024 + (size_t)(nthreads / 32) * E3_STAGES * E3_TILE_BYTES : 0) + E3_RING_BYTES;
+    return 2048 + 2048 + (tma ? (size_t)(nthreads / 32) * E3_STAGES * E3_TILE_BYTES : 0) + (size_t)E3_RING_W * E3_RING_S;
 }
 
-// All calls handled here are FULL chunks (g.chunk bytes, a multiple of 16); a shorter last call of the batch is coded by
-// k_rcs2_enc_tail after this kernel.  n_calls counts the full calls only.
+// phase timing probe (tools/enc_phases.py): when set, every warp records globaltimer at its phase boundaries
+__device__ unsigned long long *g_e3_times = nullptr;
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define E3_STAMP(k) do { if (tp && lane == 0) tp[k] = gtime(); } while (0)
+
+// g.chunk is a multiple of 16.  The tensor map covers the FULL calls only (a shorter last call would make TMA read past the
+// end of the caller's buffer): the two lanes of a short last call load their bytes directly and run the generic remainder.
 template <bool TMA>
-__global__ void __launch_bounds__(LPC_MAX_NT, 2)
+__global__ void __launch_bounds__(E3_MAX_NT, 1)
 k_rcs2_enc3(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ in, Geom g, size_t n_calls,
             const EncTab2 *__restrict__ tab, uint8_t *__restrict__ slots, size_t slot_stride, unsigned calls_per_cta,
             volatile unsigned long long *__restrict__ lb, uint64_t *__restrict__ out_off, uint8_t *__restrict__ out, unsigned flags) {
-    __shared__ __align__(16) uint2 ctab[256];
     __shared__ uint64_t bar;
-    __shared__ uint64_t fullbar[(LPC_MAX_NT / 32) * E3_STAGES];
-    __shared__ uint32_t s_len[LPC_MAX_NT / 2], s_alen[LPC_MAX_NT / 2], s_blen[LPC_MAX_NT / 2], s_excl[LPC_MAX_NT / 2];
-    constexpr int NW = LPC_MAX_NT / 32;
+    __shared__ uint64_t fullbar[(E3_MAX_NT / 32) * E3_STAGES];
+    __shared__ uint32_t s_len[E3_MAX_NT / 2], s_alen[E3_MAX_NT / 2], s_boff[E3_MAX_NT / 2], s_blen[E3_MAX_NT / 2], s_excl[E3_MAX_NT / 2];
+    __shared__ uint32_t s_prog[32];                                                        // blocks done per warp (pacing)
+    constexpr int NW = E3_MAX_NT / 32;
     __shared__ uint32_t s_wsum[NW + 1];
     __shared__ unsigned long long s_base;
     __shared__ unsigned s_tile;
     extern __shared__ __align__(16) uint8_t dyn[];
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned long long *tp = g_e3_times ? g_e3_times + ((size_t)blockIdx.x * 32 + wid) * 8 : nullptr;
+    E3_STAMP(0);
     const uint32_t dyn0 = smem_u32(dyn);
-    const uint32_t tiles0 = TMA ? ((dyn0 + 1023u) & ~1023u) : dyn0;                       // 128-byte swizzle wants 1 KB aligned tiles
-    const uint32_t ring0 = TMA ? tiles0 + (blockDim.x >> 5) * E3_STAGES * E3_TILE_BYTES : dyn0;
+    const uint32_t tb = (dyn0 + 2047u) & ~2047u;                                           // symbol table, 2 KB aligned: its address is OR-ed into the entry offsets
+    uint2 *ctab = (uint2 *)(dyn + (tb - dyn0));
+    const uint32_t tiles0 = tb + 2048;                                                     // 128-byte swizzle wants 1 KB aligned tiles
+    const uint32_t ring0 = TMA ? tiles0 + (blockDim.x >> 5) * E3_STAGES * E3_TILE_BYTES : tiles0;
+    if (threadIdx.x < 32) s_prog[threadIdx.x] = threadIdx.x < (blockDim.x >> 5) ? 0u : 0xffffffffu;
     if (threadIdx.x == 0) {
         s_tile = (unsigned)atomicAdd((unsigned long long *)(lb + gridDim.x), 1ull);     // tile index in arrival order (look-back safe)
-        tma_fetch(ctab, tab->e, sizeof ctab, &bar);
+        tma_fetch(ctab, tab->e, 2048, &bar);
         if (TMA) {
             for (unsigned k = 0; k < (blockDim.x >> 5) * E3_STAGES; k++)
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&fullbar[k])));
@@ -143,24 +163,28 @@ k_rcs2_enc3(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict_
     const size_t j0 = (size_t)bid * calls_per_cta, j = j0 + (threadIdx.x >> 1);
     const unsigned c = threadIdx.x & 1, r = threadIdx.x >> 1;
     const bool live = j < n_calls && r < calls_per_cta;
-    const uint32_t n = (uint32_t)g.chunk;                                                  // every call here is a full chunk
-    const uint32_t nb = n >> 4;                                                            // 16-byte blocks per call (8 symbols per lane each)
+    const bool is_tail = live && j * g.chunk + g.chunk > g.total;                          // the last call of the batch when it is shorter than a chunk
+    const uint32_t n = is_tail ? (uint32_t)(g.total - j * g.chunk) : (uint32_t)g.chunk;
+    const uint32_t nb = n >> 4, nbmax = (uint32_t)(g.chunk >> 4);                          // 16-byte blocks of this call / of a full call (8 symbols per lane each)
     const uint32_t fb0 = smem_u32(&fullbar[wid * E3_STAGES]);
     const uint32_t mytiles = tiles0 + wid * E3_STAGES * E3_TILE_BYTES;
     const int row0 = (int)(j0 + wid * 16);                                                 // first call (tensor row) of this warp
-    const uint32_t nst = (n + 127) >> 7;
+    const uint32_t nst = ((uint32_t)g.chunk + 127) >> 7;
     if (TMA && lane == 0) {
         tma_tile_2d(mytiles, &tmap, 0, row0, fb0);
         if (nst > 1) tma_tile_2d(mytiles + E3_TILE_BYTES, &tmap, 128, row0, fb0 + 8);
     }
     tma_wait(&bar);
+    E3_STAMP(1);
     uint8_t *slot = slots + (live ? j : 0) * slot_stride;
     const int64_t thr = rc_thr(n);
     const uint32_t b1ref = n < 4 ? 4 : 4 + (uint32_t)((((size_t)n - 4) * 37) / 64);       // rccdf.c:126
     const uint32_t b1 = (b1ref + 64 + 15) & ~15u;                                          // coder 1 lives at slot + b1 + 4 (word 0 of its image = scratch)
     uint4 *gq = (uint4 *)(slot + (c ? b1 : 0));                                            // image of this coder in the slot: [scratch word][stream words ...]
-    const uint32_t ringlane = ring0 + threadIdx.x * 4;
-    const uint32_t tb = smem_u32(ctab);
+    const uint32_t ringlane = ring0 + threadIdx.x * 4;                                     // ring: word-major, lane-minor
+    constexpr uint32_t rs = E3_RING_S;
+    const uint32_t progaddr = smem_u32(s_prog);
+    const uint32_t psel = c ? 0x4341u : 0x4240u;                                         // byte_perm selector: this coder's two symbols of a word
     // own half of OVERFLOWI (rccdf.c:46,133) as a word count: coder 1 fires when b1ref + 4 wr >= thr, coder 0 when 4 + 4 wr >= b1ref
     const int64_t lim64 = c ? (thr - (int64_t)b1ref + 3) >> 2 : ((int64_t)b1ref - 4 + 3) >> 2;
     const uint32_t limw = lim64 < 0 ? 0u : (uint32_t)lim64;
@@ -170,70 +194,129 @@ k_rcs2_enc3(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict_
     const uint8_t *ip = in + (live ? j : 0) * g.chunk;
     const uint32_t lrow = lane >> 1;                                                       // row of this lane inside the warp tile
     const uint32_t rowaddr = mytiles + lrow * 128, sw = (lrow & 7) << 4;
+    const bool ldg = !TMA || is_tail;                                                      // the short last call is not part of the tensor: its two lanes load directly
     uint4 cur = make_uint4(0, 0, 0, 0), nxt = cur;
-    if (!TMA && nb && !raw) { cur = ldg128(ip); nxt = nb > 1 ? ldg128(ip + 16) : cur; }
+    if (ldg && nb && !raw) nxt = ldg128(ip);
+    // after every block (or single symbol, in the remainder of a short call): count the new words, test this coder's half of
+    // OVERFLOWI (the tested quantity only grows, so testing less often than the reference decides the same), and let four
+    // finished words (ring image positions dr .. dr+3) leave as one 128-bit store
+    auto account = [&](uint32_t k0) {
+        wr += (e.k - k0) >> 29;
+        raw |= wr >= limw;
+        if (wr - dr >= 4) {
+            const uint32_t ra = ringlane + (dr & 4) * rs;
+            uint4 v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.x) : "r"(ra));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.y) : "r"(ra + rs));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.z) : "r"(ra + 2 * rs));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.w) : "r"(ra + 3 * rs));
+            e.nz = min(min(e.nz, min(v.x, v.y)), min(v.z, v.w));                           // zero word => walk-back case (see RcE96)
+            if (!raw) { gq[dr >> 2] = v; dr += 4; } else wr = dr + (wr & 3);               // a raw lane keeps coding but stops storing (its image is never read)
+        }
+    };
 #pragma unroll 1
     for (uint32_t st = 0; st < nst; st++) {
         if (TMA) mbar_wait(fb0 + (st & 1) * 8, (st >> 1) & 1);
-        const uint32_t cmax = min(8u, nb - st * 8);
+        const uint32_t cmax = min(8u, nbmax - st * 8);
 #pragma unroll 1
         for (uint32_t cc = 0; cc < cmax; cc++) {
+            const uint32_t b = st * 8 + cc;
             if (TMA) {
                 const uint32_t a = (rowaddr + (st & 1) * E3_TILE_BYTES) | ((cc << 4) ^ sw);
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(cur.x), "=r"(cur.y), "=r"(cur.z), "=r"(cur.w) : "r"(a));
             }
-            const uint32_t b = st * 8 + cc;
-            uint4 nxt2 = nxt;
-            if (!TMA && b + 2 < nb && !raw) nxt2 = ldg128(ip + (size_t)(b + 2) * 16);
-            const uint32_t w[4] = { cur.x >> (8 * c), cur.y >> (8 * c), cur.z >> (8 * c), cur.w >> (8 * c) };
-            uint32_t tx[8], ty[8];
+            if (ldg) { cur = nxt; if (b + 1 < nb && !raw) nxt = ldg128(ip + (size_t)(b + 1) * 16); }
+            if (b < nb) {                                                                  // (false only for the lanes of a short last call)
+                const uint32_t w[4] = { cur.x, cur.y, cur.z, cur.w };
+                uint32_t tx[8], ty[8];
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const uint32_t a = tb + (((q & 1) ? (w[q >> 1] >> 13) : (w[q >> 1] << 3)) & 0x7f8u);
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tx[q]), "=r"(ty[q]) : "r"(a));
-            }
-            const uint32_t k0 = e.k;
+                for (int q = 0; q < 4; q++) {                                              // two symbols per word: entry offsets 8 * byte, table base OR-ed / added in
+                    const uint32_t d8 = __byte_perm(w[q], 0, psel) << 3;
+                    uint32_t a0, a1;
+                    asm("lop3.b32 %0, %1, 0xffff, %2, 0xEA;" : "=r"(a0) : "r"(d8), "r"(tb));   // (d8 & 0xffff) | tb
+                    asm("mad.hi.u32 %0, %1, 65536, %2;" : "=r"(a1) : "r"(d8), "r"(tb));         // (d8 >> 16) + tb
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tx[2 * q]), "=r"(ty[2 * q]) : "r"(a0));
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(tx[2 * q + 1]), "=r"(ty[2 * q + 1]) : "r"(a1));
+                }
+                const uint32_t k0 = e.k;
 #pragma unroll
-            for (int q = 0; q < 8; q++) e.encode(tx[q], ty[q], ringlane);
-            wr += (e.k - k0) >> 29;                                                        // <= 4 words per block
-            raw |= wr >= limw;                                                             // once per block: the tested quantity only grows
-            if (wr - dr >= 4) {                                                            // four finished words (ring image positions dr .. dr+3) leave as one 128-bit store
-                const uint32_t ra = ringlane + (dr & 4) * E3_RING_S;
-                uint4 v;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.x) : "r"(ra));
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.y) : "r"(ra + E3_RING_S));
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.z) : "r"(ra + 2 * E3_RING_S));
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.w) : "r"(ra + 3 * E3_RING_S));
-                if (!raw) { gq[dr >> 2] = v; dr += 4; } else wr = dr + (wr & 3);           // a raw lane keeps coding but stops storing (its image is never read)
+                for (int q = 0; q < 8; q++) e.encode(tx[q], ty[q], ringlane);
+                account(k0);
             }
-            if (!TMA) { cur = nxt; nxt = nxt2; }
+            // Pacing.  The warp scheduler is not fair (it favours some warp slots), so identical warps drift apart: without this
+            // the first warp of a CTA finished its chunk after 64 us and the last after 126 us.  Every fourth block a warp
+            // publishes its block count and naps while it is more than E3_LEAD blocks ahead of the slowest warp of the CTA: the
+            // issue slots go to the laggards and all warps reach the layout epilogue together.  (The slowest never waits.)
+            if ((b & 3) == 3) {
+                if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(progaddr + wid * 4), "r"(b) : "memory");
+                for (;;) {
+                    uint32_t pv;
+                    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(pv) : "r"(progaddr + lane * 4) : "memory");
+                    if (b <= __reduce_min_sync(0xffffffffu, pv) + E3_LEAD) break;
+                    __nanosleep(256);
+                }
+            }
         }
         if (TMA) {
             __syncwarp();
             if (lane == 0 && st + 2 < nst) tma_tile_2d(mytiles + (st & 1) * E3_TILE_BYTES, &tmap, (int)(st + 2) * 128, row0, fb0 + (st & 1) * 8);
         }
     }
+    if (is_tail && !raw) {                                                                 // short last call: the pairs beyond its last 16-byte block (rccdf.c:129-134)
+        for (uint32_t i = nb * 16 + c; i < (n & ~1u); i += 2) {
+            const uint2 t = ctab[ip[i]];
+            const uint32_t k0 = e.k;
+            e.encode(t.x, t.y, ringlane);
+            account(k0);
+        }
+    }
+    if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" :: "r"(progaddr + wid * 4), "r"(0xffffffffu) : "memory");
+    E3_STAMP(2);
     raw = __shfl_xor_sync(0xffffffffu, (int)raw, 1) || raw;                                // either half fired -> raw copy
-    if (!raw) {                                                                            // rceflush turborc_.h:118-128 (n is even: no odd tail)
+    if (!raw) {
+        if (is_tail && c == 0 && (n & 1)) {                                                // odd tail on coder 0 (rccdf.c:135-136); at most one more word
+            const uint2 t = ctab[ip[n - 1]];
+            const uint32_t k0 = e.k;
+            e.encode(t.x, t.y, ringlane);
+            wr += (e.k - k0) >> 29;
+            if (wr - dr >= 4) {
+                const uint32_t ra = ringlane + (dr & 4) * rs;
+                uint4 v;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.x) : "r"(ra));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.y) : "r"(ra + rs));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.z) : "r"(ra + 2 * rs));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.w) : "r"(ra + 3 * rs));
+                e.nz = min(min(e.nz, min(v.x, v.y)), min(v.z, v.w));
+                gq[dr >> 2] = v; dr += 4;
+            }
+        }
+        // rceflush turborc_.h:118-128
         if (e.rh == 0) { e96_put(e, e.lh, ringlane, wr); e.lh = e.ll; e.ll = 0; e.rh = e.rl; e.rl = 0; }
         if (e.rh > 2u || (e.rh == 2u && e.rl != 0)) { e96_add(e, 0, 1); e96_put(e, e.lh, ringlane, wr); }   // range > 2^33
         else { e96_add(e, 1, 0); e96_put(e, e.lh, ringlane, wr); e96_put(e, e.ll, ringlane, wr); }
-        asm volatile("st.shared.u32 [%0], %1;" :: "r"(ringlane + (wr & (E3_RING_W - 1)) * E3_RING_S), "r"(e.pend) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" :: "r"(ringlane + (wr & (E3_RING_W - 1)) * rs), "r"(e.pend) : "memory");
+        e.nz = min(e.nz, e.pend);
         // image positions dr .. wr are still in the ring (<= 3 + 3 + 1 words): two more 128-bit stores cover them
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const uint32_t ra = ringlane + ((dr + 4 * h) & 4) * E3_RING_S;
+            const uint32_t ra = ringlane + ((dr + 4 * h) & 4) * rs;
             uint4 v;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.x) : "r"(ra));
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.y) : "r"(ra + E3_RING_S));
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.z) : "r"(ra + 2 * E3_RING_S));
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.w) : "r"(ra + 3 * E3_RING_S));
-            if (dr + 4 * h <= wr) gq[(dr >> 2) + h] = v;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.y) : "r"(ra + rs));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.z) : "r"(ra + 2 * rs));
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v.w) : "r"(ra + 3 * rs));
+            const uint32_t p0 = dr + 4 * h;                                                // words put by the loop but not drained yet: zero check on the valid ones
+            if (p0 <= wr) e.nz = min(e.nz, v.x);
+            if (p0 + 1 <= wr) e.nz = min(e.nz, v.y);
+            if (p0 + 2 <= wr) e.nz = min(e.nz, v.z);
+            if (p0 + 3 <= wr) e.nz = min(e.nz, v.w);
+            if (p0 <= wr) gq[(dr >> 2) + h] = v;
         }
     }
     const uint32_t mypos = wr * 4, other = __shfl_xor_sync(0xffffffffu, mypos, 1);         // stream bytes of this coder / of its partner
-    const uint32_t rare = e.rare | __shfl_xor_sync(0xffffffffu, e.rare, 1);
-    if (c == 0 && r < LPC_MAX_NT / 2) {
+    // words still in the ring when the loop ended were checked on their way out (e96_put) or are checked here
+    const uint32_t rare = (e.nz == 0 ? 1u : 0u) | __shfl_xor_sync(0xffffffffu, e.nz == 0 ? 1u : 0u, 1);
+    if (c == 0 && r < E3_MAX_NT / 2) {
         UnitMeta m; m.a_off = 0; m.a_len = 0; m.b_off = b1 + 4; m.b_len = 0; m.len = 0; m.flags = 0;
         if (live) {
             const uint32_t p0 = mypos, p1 = other;
@@ -249,9 +332,11 @@ k_rcs2_enc3(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict_
                 }
             } else { m.a_len = raw ? 0 : 4 + p0; m.b_len = raw ? 0 : p1; m.len = raw ? n : 4 + p0 + p1; m.flags = raw ? UM_RAW : 0; }
         }
-        s_len[r] = m.len; s_alen[r] = (m.flags & UM_RAW) ? 0xffffffffu : m.a_len; s_blen[r] = m.b_len;
+        s_len[r] = m.len; s_alen[r] = (m.flags & UM_RAW) ? 0xffffffffu : m.a_len; s_boff[r] = m.b_off; s_blen[r] = m.b_len;
     }
+    E3_STAMP(3);
     __syncthreads();
+    E3_STAMP(4);
     // ---- exclusive scan of the call lengths of this CTA (calls_per_cta <= 256: thread t scans entry t)
     uint32_t v = threadIdx.x < calls_per_cta ? s_len[threadIdx.x] : 0, inc = v;
 #pragma unroll
@@ -291,49 +376,34 @@ k_rcs2_enc3(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict_
     }
     __syncthreads();
     const unsigned long long base = s_base;
+    E3_STAMP(5);
     if (threadIdx.x < calls_per_cta && j0 + threadIdx.x < n_calls) out_off[j0 + threadIdx.x] = base + s_excl[threadIdx.x];
     if (threadIdx.x == 0 && j0 + calls_per_cta >= n_calls) out_off[n_calls] = base + s_wsum[NW];
-    // ---- layout: a warp per call, pieces from the slot (or the input, for a raw call) to their final place
-    for (unsigned q = wid; q < calls_per_cta && j0 + q < n_calls; q += blockDim.x >> 5) {
+    // ---- layout: EIGHT lanes per call (four calls per warp at a time: the copy is latency-bound, so what counts is how many
+    // loads each lane keeps in flight), pieces from the slot (or the input, for a raw call) to their final place
+    const unsigned sub = lane & 7, grp = lane >> 3;
+    for (unsigned q = wid * 4 + grp; q < calls_per_cta && j0 + q < n_calls; q += (blockDim.x >> 5) * 4) {
         uint8_t *dst = out + base + s_excl[q];
         uint8_t *sl = slots + (j0 + q) * slot_stride;
-        if (s_alen[q] == 0xffffffffu) { group_copy4(dst, in + (j0 + q) * g.chunk, n, lane, 32); continue; }
-        if (lane == 0) *(uint32_t *)sl = s_alen[q] - 4;                                    // len0 header (rccdf.c:141) over the scratch word
-        __syncwarp();
+        if (s_alen[q] == 0xffffffffu) { group_copy4(dst, in + (j0 + q) * g.chunk, s_len[q], sub, 8); continue; }
         if (((uintptr_t)dst & 3) == 0) {
-            const uint32_t *pa = (const uint32_t *)sl, *pb = (const uint32_t *)(sl + b1 + 4);
-            const uint32_t wa = s_alen[q] >> 2, W = wa + (s_blen[q] >> 2);
+            const uint32_t *pa = (const uint32_t *)sl, *pb = (const uint32_t *)(sl + s_boff[q]);
+            const uint32_t wa = s_alen[q] >> 2, W = wa + (s_blen[q] >> 2), len0 = s_alen[q] - 4;   // word 0 = the len0 header (rccdf.c:141)
             uint32_t *d = (uint32_t *)dst;
-            for (uint32_t w0 = 0; w0 < W; w0 += LB_U * 32) {
+            for (uint32_t w0 = 0; w0 < W; w0 += LB_U * 8) {
                 uint32_t vv[LB_U];
 #pragma unroll
-                for (int k = 0; k < LB_U; k++) { const uint32_t w = w0 + k * 32 + lane; vv[k] = w < wa ? pa[w] : (w < W ? pb[w - wa] : 0u); }
+                for (int k = 0; k < LB_U; k++) { const uint32_t w = w0 + k * 8 + sub; vv[k] = w == 0 ? len0 : (w < wa ? pa[w] : (w < W ? pb[w - wa] : 0u)); }
 #pragma unroll
-                for (int k = 0; k < LB_U; k++) { const uint32_t w = w0 + k * 32 + lane; if (w < W) d[w] = vv[k]; }
+                for (int k = 0; k < LB_U; k++) { const uint32_t w = w0 + k * 8 + sub; if (w < W) __stcs(d + w, vv[k]); }
             }
-        } else { group_copy(dst, sl, s_alen[q], lane, 32); if (s_blen[q]) group_copy(dst + s_alen[q], sl + b1 + 4, s_blen[q], lane, 32); }
+        } else {
+            if (sub == 0) *(uint32_t *)sl = s_alen[q] - 4;
+            __syncwarp(0xffu << (grp * 8));
+            group_copy(dst, sl, s_alen[q], sub, 8); if (s_blen[q]) group_copy(dst + s_alen[q], sl + s_boff[q], s_blen[q], sub, 8);
+        }
     }
-}
-
-// The last call of a batch when it is shorter than a chunk: one warp, generic coder (any length, walk-back carry), placed
-// behind the full calls.  Runs after k_rcs2_enc3 on the same stream (out_off[n_full] is the running total it left).
-__global__ void k_rcs2_enc_tail(const uint8_t *__restrict__ in, Geom g, size_t n_full, const EncTab2 *__restrict__ tab,
-                                uint8_t *__restrict__ slots, size_t slot_stride, uint64_t *__restrict__ out_off, uint8_t *__restrict__ out) {
-    __shared__ uint32_t ctab[256];
-    __shared__ UnitMeta sm;
-    for (unsigned x = threadIdx.x; x < 256; x += blockDim.x) ctab[x] = tab->e[x].x | tab->e[x].y << 16;
-    __syncwarp();
-    size_t start, n; call_span(g, n_full, start, n);
-    uint8_t *slot = slots + n_full * slot_stride;
-    if (threadIdx.x == 0) { UnitMeta m; rc_static_enc_call<2, true>(in + start, n, ctab, nullptr, slot, m); sm = m; }
-    __syncwarp();
-    const UnitMeta m = sm;
-    const uint64_t o = n_full ? out_off[n_full] : 0;
-    if (n_full == 0 && threadIdx.x == 0) out_off[0] = 0;
-    uint8_t *dst = out + o;
-    if (m.flags & UM_RAW) group_copy(dst, in + start, n, threadIdx.x, 32);
-    else { group_copy(dst, slot, m.a_len, threadIdx.x, 32); if (m.b_len) group_copy(dst + m.a_len, slot + m.b_off, m.b_len, threadIdx.x, 32); }
-    if (threadIdx.x == 0) out_off[n_full + 1] = o + m.len;
+    E3_STAMP(6);
 }
 
 }  // namespace trc

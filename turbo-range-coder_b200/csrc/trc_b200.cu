@@ -91,6 +91,16 @@ static void lpc_shape(size_t n_calls, size_t cpc, unsigned &calls_per_cta, unsig
     if (cpc == 0 && per_sm > LPC_NT / 2 && k >= 1 && k <= 3) calls_per_cta = (unsigned)((n_calls + (size_t)n_sm * k - 1) / ((size_t)n_sm * k));
     ctas = (unsigned)((n_calls + calls_per_cta - 1) / calls_per_cta);
 }
+// k_rcs2_enc3: ONE CTA per SM (its warps pace each other through shared memory), up to 384 calls = 24 warps each; batches
+// of at most one wave are split evenly over the SMs, bigger ones run in waves of full CTAs
+static void e3_shape(size_t n_calls, unsigned &calls_per_cta, unsigned &ctas) {
+    const size_t n_sm = (size_t)sm_count(), cap = E3_MAX_NT / 2;
+    size_t per = (n_calls + n_sm - 1) / n_sm;
+    if (per > cap) per = cap;
+    if (per < 16) per = 16;
+    calls_per_cta = (unsigned)per;
+    ctas = (unsigned)((n_calls + per - 1) / per);
+}
 // lane-per-call v2 kernels: threads per CTA (one call per thread), same balancing idea
 static unsigned v2_shape(size_t n_calls, size_t cpc) {
     unsigned cpcta, ctas; lpc_shape(n_calls, cpc, cpcta, ctas);           // calls per CTA if the batch is about one wave
@@ -130,7 +140,7 @@ static int make_plan(int codec, size_t total_len, size_t chunk_len, Plan &p) {
     p.off_o1 = o;    o += al256(p.o1_threads * O1_TAB_WORDS * 4);
     // room for one TableSet per V2_NT calls is the worst case the v2 path accepts (cpc >= V2_NT)
     p.off_tabs = o;  o += codec_static(codec) ? al256(((p.g.n_calls + V2_NT - 1) / V2_NT) * sizeof(TableSet)) : 0;
-    p.off_lb = o;    o += codec == RCS2 ? al256((p.g.n_calls / (LPC_NT / 2) + 3) * 8) : 0;   // look-back words of the fused encoder + tile counter
+    p.off_lb = o;    o += codec == RCS2 ? al256((p.g.n_calls / 16 + 3) * 8) : 0;   // look-back words of the fused encoder + tile counter
     p.total = o;
     return TRC_OK;
 }
@@ -140,8 +150,8 @@ static int dev_attrs() {
     static bool done[MAX_DEV];
     const int d = cur_dev();
     if (done[d]) return TRC_OK;
-    CK(cudaFuncSetAttribute(k_rcs2_enc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem_bytes(LPC_MAX_NT, true)));
-    CK(cudaFuncSetAttribute(k_rcs2_enc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem_bytes(LPC_MAX_NT, false)));
+    CK(cudaFuncSetAttribute(k_rcs2_enc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem_bytes(E3_MAX_NT, true)));
+    CK(cudaFuncSetAttribute(k_rcs2_enc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem_bytes(E3_MAX_NT, false)));
     done[d] = true;
     return TRC_OK;
 }
@@ -246,34 +256,30 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     TableSet *tabs = (TableSet *)(sc + p.off_tabs);
     const bool fused = g_fused && codec == RCS2 && v2 && chunks_per_cdf == 0;
     if (fused) {                 // TRC_RCS2, one table: coder + offsets + layout in ONE kernel (rcs2_v3.cuh)
-        const size_t n_full = total_len / chunk_len;                        // full chunks; a shorter last call goes to the tail kernel
-        const bool tail = total_len % chunk_len != 0;
+        const size_t n_full = total_len / chunk_len;                        // the tensor map covers full chunks only (see rcs2_v3.cuh)
         EncTab2 *t2 = (EncTab2 *)tabs;
         unsigned cpcta = 0, ctas = 0;
-        if (n_full) lpc_shape(n_full, 0, cpcta, ctas);
+        e3_shape(g.n_calls, cpcta, ctas);
         k_build_enctab2<<<1, 256, 0, st>>>(d_cdf, cdfnum, t2, (unsigned long long *)(sc + p.off_lb), ctas + 1);
         CK_LAUNCH();
         prof_mark(st);
-        if (n_full) {
-            const unsigned nt = (2 * cpcta + 31) & ~31u;
-            const bool tma = g_enc_tma && tmap_encode() && n_full < (1ull << 31);
-            CUtensorMap tm; memset(&tm, 0, sizeof tm);
-            if (tma) {                                                      // input as a 2-D tensor [calls][chunk bytes], box = 16 calls x 128 bytes
-                const cuuint64_t dims[2] = { (cuuint64_t)chunk_len, (cuuint64_t)n_full }, strides[1] = { (cuuint64_t)chunk_len };
-                const cuuint32_t box[2] = { 128, 16 }, estr[2] = { 1, 1 };
-                CUresult r = tmap_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)d_in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled failed (%d)", (int)r); return TRC_E_CUDA; }
-            }
-            const size_t smem = e3_smem_bytes(nt, tma);
-            rc = dev_attrs(); if (rc) return rc;
-            if (tma) k_rcs2_enc3<true><<<ctas, nt, smem, st>>>(tm, d_in, g, n_full, t2, slots, p.slot_stride, cpcta,
-                                                              (volatile unsigned long long *)(sc + p.off_lb), d_out_off, d_out, g_force_redo ? 1u : 0u);
-            else     k_rcs2_enc3<false><<<ctas, nt, smem, st>>>(tm, d_in, g, n_full, t2, slots, p.slot_stride, cpcta,
-                                                               (volatile unsigned long long *)(sc + p.off_lb), d_out_off, d_out, g_force_redo ? 1u : 0u);
-            CK_LAUNCH();
+        const unsigned nt = (2 * cpcta + 31) & ~31u;
+        const bool tma = g_enc_tma && n_full && tmap_encode() && n_full < (1ull << 31);
+        CUtensorMap tm; memset(&tm, 0, sizeof tm);
+        if (tma) {                                                          // input as a 2-D tensor [calls][chunk bytes], box = 16 calls x 128 bytes
+            const cuuint64_t dims[2] = { (cuuint64_t)chunk_len, (cuuint64_t)n_full }, strides[1] = { (cuuint64_t)chunk_len };
+            const cuuint32_t box[2] = { 128, 16 }, estr[2] = { 1, 1 };
+            CUresult r = tmap_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)d_in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof g_err, "cuTensorMapEncodeTiled failed (%d)", (int)r); return TRC_E_CUDA; }
         }
-        if (tail) { k_rcs2_enc_tail<<<1, 32, 0, st>>>(d_in, g, n_full, t2, slots, p.slot_stride, d_out_off, d_out); CK_LAUNCH(); }
+        const size_t smem = e3_smem_bytes(nt, tma);
+        rc = dev_attrs(); if (rc) return rc;
+        if (tma) k_rcs2_enc3<true><<<ctas, nt, smem, st>>>(tm, d_in, g, g.n_calls, t2, slots, p.slot_stride, cpcta,
+                                                          (volatile unsigned long long *)(sc + p.off_lb), d_out_off, d_out, g_force_redo ? 1u : 0u);
+        else     k_rcs2_enc3<false><<<ctas, nt, smem, st>>>(tm, d_in, g, g.n_calls, t2, slots, p.slot_stride, cpcta,
+                                                           (volatile unsigned long long *)(sc + p.off_lb), d_out_off, d_out, g_force_redo ? 1u : 0u);
+        CK_LAUNCH();
         prof_mark(st); prof_mark(st); prof_mark(st);
         return TRC_OK;
     }
@@ -430,6 +436,13 @@ int trc_cdfini_batch_dev(const unsigned char *d_in, size_t total_len, size_t chu
     cudaError_t e = cudaPeekAtLastError();
     cudaFreeAsync(hist, st);
     CK(e);
+    return TRC_OK;
+}
+
+// phase timing probe of k_rcs2_enc3 (tools/enc_phases.py): d_buf = ctas x 16 warps x 8 uint64, or NULL to switch it off
+int trc_debug_enc_times(void *d_buf) {
+    unsigned long long *p = (unsigned long long *)d_buf;
+    CK(cudaMemcpyToSymbol(g_e3_times, &p, sizeof p));
     return TRC_OK;
 }
 
