@@ -406,4 +406,180 @@ k_rcs2_enc3(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict_
     E3_STAMP(6);
 }
 
+
+// =========================================================================================================================
+// TRC_RCS2 decoder (rccdfsb2dec, rccdf.c:166-184), lane per coder.  Same plan as k_rcs2_dec_lpc (speculative symbol from an fp32
+// estimate of code / range, exact 64-bit verification, per-block redo by the reference's binary search) with a shorter step:
+//   * ONE unsigned test covers both ways the estimate can be wrong: x is right  <=>  0 <= code - cdf[x]*range < freq[x]*range.
+//     If x is too high the subtraction wraps to >= 2^64 - freq[x-1]*range, which is still >= freq[x]*range because
+//     (freq[x-1] + freq[x]) * range <= 2^15 * range < 2^64; so `code - rp >= fr` (unsigned) flags both cases.
+//   * floor() of the quotient comes out of the FMA itself (round-down mode into the 2^23 integer grid): no separate add.
+//   * {cdf, freq} is one 8-byte table entry; the stream ring is addressed like the encoder's (cursor in the top bits of a
+//     register: wraps for free, address = one shift-and-add); one word of look-ahead instead of two.
+// =========================================================================================================================
+constexpr int      D3_RING_W = 16;
+constexpr uint32_t D3_RING_S = 2048;                    // bytes between consecutive ring words of a lane (512 lanes)
+struct __align__(16) DecTab2 { uint2 e[256]; uint8_t lut[PROB_TOTAL]; };   // {cdf, freq} per symbol; slot -> symbol
+
+__global__ void __launch_bounds__(1024)
+k_build_dectab2(const cdf_t *__restrict__ cdf, unsigned cdfnum, DecTab2 *__restrict__ ts) {
+    __shared__ uint16_t scdf[CDF_STRIDE];
+    const cdf_t *c0 = cdf + (size_t)blockIdx.x * CDF_STRIDE;
+    DecTab2 &t = ts[blockIdx.x];
+    for (unsigned x = threadIdx.x; x <= cdfnum; x += blockDim.x) scdf[x] = c0[x];
+    __syncthreads();
+    if (blockIdx.y == 0) {
+        for (unsigned x = threadIdx.x; x < 256; x += blockDim.x) {
+            uint32_t c = 0, f = 0;
+            if (x < cdfnum) { c = scdf[x]; f = (uint32_t)scdf[x + 1] - c; }
+            t.e[x] = make_uint2(c, f);
+        }
+        return;
+    }
+    const unsigned per = PROB_TOTAL / LUT_PARTS, r0 = (blockIdx.y - 1) * per;
+    for (unsigned r = r0 + threadIdx.x; r < r0 + per; r += blockDim.x) {
+        unsigned x = 0, hi = cdfnum;
+        while (x + 1 < hi) { unsigned mid = (x + hi) >> 1; if (scdf[mid] <= r) x = mid; else hi = mid; }
+        t.lut[r] = (uint8_t)x;
+    }
+}
+
+struct RcD3 {
+    uint32_t rl, rh, cl, ch;        // range, code
+    uint32_t n0;                    // the next stream word (already in a register)
+    uint32_t k;                     // ring cursor: (index of the word after n0, mod 16) << 28
+    bool bad;
+    __device__ __forceinline__ uint32_t step(const uint8_t *lut, const uint2 *dtab, uint32_t ringlane) {
+        rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;                    // _rccdfrange
+        float qf;                                                                     // floor(code / range) in the low mantissa bits (fix-up by verification)
+        asm("fma.rm.f32 %0, %1, %2, 0f4B400000;" : "=f"(qf) : "f"(__ull2float_rz((uint64_t)ch << 32 | cl)), "f"(rcp_approx(__ull2float_rn((uint64_t)rh << 32 | rl))));
+        const uint32_t x = lut[__float_as_uint(qf) & 0x7fffu];
+        const uint2 e = dtab[x];
+        const uint64_t rp = (uint64_t)rl * e.x, fr = (uint64_t)rl * e.y;
+        const uint32_t pl = (uint32_t)rp, ph = (uint32_t)(rp >> 32) + rh * e.x;       // cdf[x] * range
+        const uint32_t fl = (uint32_t)fr, fh = (uint32_t)(fr >> 32) + rh * e.y;       // freq[x] * range
+        uint32_t dl, dh;
+        asm("sub.cc.u32 %0, %2, %4;\n\tsubc.u32 %1, %3, %5;" : "=r"(dl), "=r"(dh) : "r"(cl), "r"(ch), "r"(pl), "r"(ph));
+        bad |= ((uint64_t)dh << 32 | dl) >= ((uint64_t)fh << 32 | fl);               // not (0 <= code - rp < fr): wrong symbol
+        uint32_t a;
+        asm("mad.hi.u32 %0, %1, 32768, %2;" : "=r"(a) : "r"(k), "r"(ringlane));       // (k >> 28) * 2048 + lane base
+        asm volatile("{\n\t.reg .pred p;\n\t"
+            "setp.eq.u32 p, %7, 0;\n\t"           // _rcdnorm_ turborc_.h:111
+            "selp.u32 %0, %6, %7, p;\n\t"         // rh = p ? fl : fh
+            "selp.u32 %1, 0, %6, p;\n\t"          // rl = p ? 0 : fl
+            "selp.u32 %2, %8, %9, p;\n\t"         // ch = p ? dl : dh
+            "selp.u32 %3, %4, %8, p;\n\t"         // cl = p ? n0 : dl
+            "@p ld.shared.u32 %4, [%10];\n\t"
+            "@p add.u32 %5, %5, 0x10000000;\n\t"
+            "}" : "=r"(rh), "=r"(rl), "=r"(ch), "=r"(cl), "+r"(n0), "+r"(k) : "r"(fl), "r"(fh), "r"(dl), "r"(dh), "r"(a) : "memory");
+        return x;
+    }
+};
+
+// dynamic shared memory: [DecTab2: 2 KB + 32 KB][ring: 16 words x 2 KB]
+constexpr size_t D3_SMEM = sizeof(DecTab2) + (size_t)D3_RING_W * D3_RING_S;
+
+__global__ void __launch_bounds__(512, 2)
+k_rcs2_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint8_t *__restrict__ out, Geom g,
+            size_t n_calls, const DecTab2 *__restrict__ ts, unsigned cdfnum, size_t cpc, unsigned calls_per_cta) {
+    extern __shared__ __align__(16) uint8_t dyn[];
+    DecTab2 *tabs = (DecTab2 *)dyn;
+    const uint2 *dtab = tabs->e;
+    const uint8_t *lut = tabs->lut;
+    uint32_t *ringbuf = (uint32_t *)(dyn + sizeof(DecTab2));
+    __shared__ uint64_t bar;
+    const size_t j0 = (size_t)blockIdx.x * calls_per_cta, j = j0 + (threadIdx.x >> 1);
+    const unsigned c = threadIdx.x & 1;
+    if (threadIdx.x == 0) tma_fetch(tabs, ts + (cpc ? j0 / cpc : 0), (uint32_t)sizeof(DecTab2), &bar);
+    __syncthreads();
+    tma_wait(&bar);
+    const bool live = j < n_calls && (threadIdx.x >> 1) < calls_per_cta;
+    size_t start = 0, n = 0;
+    uint64_t so = 0, sl = 0;
+    if (live) { call_span(g, j, start, n); so = in_off[j]; sl = in_off[j + 1] - so; }
+    const uint8_t *gend = in + in_off[g.n_calls], *stream = in + so;
+    uint8_t *op = out + start;
+    const bool rawc = sl == n;                                                       // raw chunk: both lanes copy half
+    if (rawc || !live) {
+        if (live) { size_t h = (n / 2) & ~(size_t)15; if (c == 0) thread_copy(op, stream, h); else thread_copy(op + h, stream + h, n - h); }
+        n = 0;                                                                       // still join the shuffles
+    }
+    uint32_t len0 = n ? ld_u32_clamped(stream, gend) : 0;
+    const uint8_t *p = stream + 4 + (c ? (len0 & ~3u) : 0);                          // stream c (rccdf.c:167)
+    if (p > gend || p < stream || n == 0) p = gend;
+    // word addressing relative to the 16-byte aligned base below p; reads past the end of the packed buffer return zero
+    const uint32_t *qbase = (const uint32_t *)((uintptr_t)p & ~(uintptr_t)15);
+    const long long wavail = ((const uint8_t *)gend - (const uint8_t *)qbase) >> 2;
+    const uint32_t wlim = wavail > 0 ? (uint32_t)(wavail - 1) : 0u;
+    const bool none = wavail <= 0;
+    auto gword = [&](uint32_t w) -> uint32_t { return (!none && w <= wlim) ? __ldg(qbase + w) : 0u; };
+    auto gquad = [&](uint32_t w) -> uint4 {                                           // w multiple of 4
+        if (!none && w + 3 <= wlim) return __ldg((const uint4 *)(qbase + w));
+        return make_uint4(gword(w), gword(w + 1), gword(w + 2), gword(w + 3));
+    };
+    uint32_t *ring = ringbuf + threadIdx.x;
+    constexpr uint32_t RS = D3_RING_S / 4;
+    const uint32_t ringlane = smem_u32(ring);
+    auto ring_put = [&](uint32_t w, const uint4 &v) {                                 // w multiple of 4
+        ring[((w + 0) & (D3_RING_W - 1)) * RS] = v.x; ring[((w + 1) & (D3_RING_W - 1)) * RS] = v.y;
+        ring[((w + 2) & (D3_RING_W - 1)) * RS] = v.z; ring[((w + 3) & (D3_RING_W - 1)) * RS] = v.w;
+    };
+    RcD3 d;
+    uint32_t fi, ci;                                                                  // words [fi-16, fi) are in the ring; ci = index of the word after n0
+    auto resync = [&](uint32_t w0, uint64_t range, uint64_t code) {                   // (re)start the ring at word w0 = next unread word
+        fi = w0 & ~3u;
+        for (int q = 0; q < 3; q++) { ring_put(fi, gquad(fi)); fi += 4; }
+        d.rl = (uint32_t)range; d.rh = (uint32_t)(range >> 32); d.cl = (uint32_t)code; d.ch = (uint32_t)(code >> 32);
+        d.n0 = ring[(w0 & (D3_RING_W - 1)) * RS];
+        ci = w0 + 1; d.k = ci << 28; d.bad = false;
+    };
+    {
+        const uint32_t w0 = (uint32_t)(((uintptr_t)p & 15) >> 2);
+        resync(w0 + 2, ~0ull, (uint64_t)gword(w0) << 32 | gword(w0 + 1));             // rcdinit turborc_.h:152-158
+    }
+    const size_t nb = n & ~(size_t)15;
+    const size_t nbmax = __reduce_max_sync(0xffffffffu, (unsigned)nb);               // warp-uniform trip count for the shuffles
+    for (size_t i = 0; i < nbmax; i += 16) {
+        uint32_t a0 = 0, a1 = 0;
+        if (i < nb) {
+            const bool need = fi - ci <= 9;                                           // top the ring up (stores happen after the block)
+            uint4 t4 = make_uint4(0, 0, 0, 0);
+            if (need) t4 = gquad(fi);
+            const RcD3 s0 = d;                                                        // block start state (for the redo path)
+#pragma unroll
+            for (int q = 0; q < 4; q++) a0 |= d.step(lut, dtab, ringlane) << (8 * q);
+#pragma unroll
+            for (int q = 0; q < 4; q++) a1 |= d.step(lut, dtab, ringlane) << (8 * q);
+            const uint32_t ci_new = ci + ((d.k - s0.k) >> 28);                        // <= 4 words per block
+            const bool dry = ci_new > fi;                                             // a read ran past the filled part of the ring
+            if (need) { ring_put(fi, t4); fi += 4; }
+            if (__builtin_expect(d.bad || dry, 0)) {                                  // estimate missed (or ring ran dry): exact redo
+                RcDExact ex;
+                ex.range = (uint64_t)s0.rh << 32 | s0.rl; ex.code = (uint64_t)s0.ch << 32 | s0.cl;
+                ex.base = qbase; ex.wlim = wlim; ex.wi = none ? 1u : ci - 1;         // n0 was word ci-1
+                a0 = a1 = 0;
+                for (int q = 0; q < 4; q++) a0 |= ex.step2(dtab, cdfnum) << (8 * q);
+                for (int q = 0; q < 4; q++) a1 |= ex.step2(dtab, cdfnum) << (8 * q);
+                resync(ex.wi, ex.range, ex.code);
+            } else ci = ci_new;
+        }
+        // a0/a1 = this coder's symbols 0-3 / 4-7 of the block; interleave with the partner's
+        uint32_t b0 = __shfl_xor_sync(0xffffffffu, a0, 1), b1 = __shfl_xor_sync(0xffffffffu, a1, 1);
+        if (i < nb) {
+            uint32_t e0 = c ? b0 : a0, o0 = c ? a0 : b0, e1 = c ? b1 : a1, o1 = c ? a1 : b1;   // even-position / odd-position symbols
+            uint2 v = c ? make_uint2(__byte_perm(e1, o1, 0x5140), __byte_perm(e1, o1, 0x7362))
+                        : make_uint2(__byte_perm(e0, o0, 0x5140), __byte_perm(e0, o0, 0x7362));
+            *(uint2 *)(op + i + 8 * c) = v;
+        }
+    }
+    // remaining full pairs, then the odd tail on coder 0 (rccdf.c:179-182): exact path
+    if (n > nb) {
+        RcDExact ex;
+        ex.range = (uint64_t)d.rh << 32 | d.rl; ex.code = (uint64_t)d.ch << 32 | d.cl;
+        ex.base = qbase; ex.wlim = wlim; ex.wi = none ? 1u : ci - 1;
+        for (size_t i = nb + c; i < (n & ~(size_t)1); i += 2) op[i] = (uint8_t)ex.step2(dtab, cdfnum);
+        if (c == 0 && (n & 1)) op[n - 1] = (uint8_t)ex.step2(dtab, cdfnum);
+    }
+}
+
 }  // namespace trc

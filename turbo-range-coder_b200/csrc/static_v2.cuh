@@ -470,6 +470,15 @@ struct RcDExact {
         if ((uint32_t)(range >> 32) == 0) { range <<= 32; code = code << 32 | fetch(); }
         return x;
     }
+    __device__ inline uint32_t step2(const uint2 *dtab, unsigned cdfnum) {          // same, table of {cdf, freq} pairs
+        range >>= PROB_BITS;
+        unsigned x = 0, hi = cdfnum;
+        while (x + 1 < hi) { unsigned mid = (x + hi) >> 1; if ((uint64_t)dtab[mid].x * range > code) hi = mid; else x = mid; }
+        const uint2 e = dtab[x];
+        code -= (uint64_t)e.x * range; range *= e.y;
+        if ((uint32_t)(range >> 32) == 0) { range <<= 32; code = code << 32 | fetch(); }
+        return x;
+    }
 };
 
 // =========================================================================================================

@@ -152,6 +152,19 @@ static int dev_attrs() {
     if (done[d]) return TRC_OK;
     CK(cudaFuncSetAttribute(k_rcs2_enc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem_bytes(E3_MAX_NT, true)));
     CK(cudaFuncSetAttribute(k_rcs2_enc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem_bytes(E3_MAX_NT, false)));
+    CK(cudaFuncSetAttribute(k_rcs2_dec3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D3_SMEM));
+    done[d] = true;
+    return TRC_OK;
+}
+
+// decode-side tables come from the stream-ordered allocator; keep its pool from trimming back to the OS at every
+// synchronisation (the default release threshold of 0 makes each call pay a fresh cuMemMap)
+static int pool_keep() {
+    static bool done[MAX_DEV];
+    const int d = cur_dev();
+    if (done[d]) return TRC_OK;
+    cudaMemPool_t pool; CK(cudaDeviceGetDefaultMemPool(&pool, d));
+    unsigned long long keep = ~0ull; CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     done[d] = true;
     return TRC_OK;
 }
@@ -350,16 +363,27 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
     auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
     g_prof_n = 0;
     if (codec == ANSW && !((((uintptr_t)d_in | (uintptr_t)d_out) & 3) == 0 && (chunks_per_cdf == 0 || chunks_per_cdf % V2_NT == 0))) return TRC_E_ARG;
+    static const int g_dec3 = getenv("TRC_DEC3") ? atoi(getenv("TRC_DEC3")) : 1;     // 0: previous generation of the TRC_RCS2 decoder (A/B runs)
+    if (codec == RCS2 && g_dec3 && v2_ok(d_out, chunk_len, chunks_per_cdf) && ((uintptr_t)d_in & 15) == 0) {
+        rc = dev_attrs(); if (rc) return rc;
+        rc = pool_keep(); if (rc) return rc;
+        DecTab2 *t2 = nullptr;
+        const size_t nt = n_tables(g.n_calls, chunks_per_cdf);
+        CK(cudaMallocAsync((void **)&t2, nt * sizeof(DecTab2), st));
+        k_build_dectab2<<<dim3((unsigned)nt, 1 + LUT_PARTS), 1024, 0, st>>>(d_cdf, cdfnum, t2);
+        g_launches++;
+        prof_mark(st);
+        unsigned cpcta, ctas; lpc_shape(g.n_calls, chunks_per_cdf, cpcta, ctas);
+        const unsigned nt2 = (2 * cpcta + 31) & ~31u;
+        k_rcs2_dec3<<<ctas, nt2, D3_SMEM, st>>>(d_in, d_in_off, d_out, g, g.n_calls, t2, cdfnum, chunks_per_cdf, cpcta);
+        g_launches++; prof_mark(st);
+        cudaError_t e = cudaPeekAtLastError();
+        cudaFreeAsync(t2, st);
+        CK(e);
+        return TRC_OK;
+    }
     if (codec == ANSW || (codec_static(codec) && v2_ok(d_out, chunk_len, chunks_per_cdf) && ((uintptr_t)d_in & 15) == 0)) {
-        // decode-side tables come from the stream-ordered allocator; keep its pool from trimming back to the OS
-        // at every synchronisation (the default release threshold of 0 makes each call pay a fresh cuMemMap)
-        static int s_pool_dev = -1;
-        int dev = 0; CK(cudaGetDevice(&dev));
-        if (dev != s_pool_dev) {
-            cudaMemPool_t pool; CK(cudaDeviceGetDefaultMemPool(&pool, dev));
-            unsigned long long keep = ~0ull; CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-            s_pool_dev = dev;
-        }
+        rc = pool_keep(); if (rc) return rc;
         TableSet *tabs = nullptr;
         const size_t nt = n_tables(g.n_calls, chunks_per_cdf);
         CK(cudaMallocAsync((void **)&tabs, nt * sizeof(TableSet), st));
