@@ -259,6 +259,7 @@ def run_extras(trc, torch, dev, d_zipf, cdf_dev, flush, main_chunk):
     for chunk in sorted({main_chunk, 4096, 65536, 1 << 20}):
         b = trc.DeviceBatch(CODECS["rcs2"], size, chunk, cdfnum=256, device=dev)
         b.cdf = cdf_dev
+        b.prebuild_tables()
         b.encode(d_zipf); back = b.decode(); torch.cuda.synchronize()
         assert torch.equal(back, d_zipf)
         e, d = time_batch(trc, torch, b, d_zipf, flush, 3 if chunk >= 65536 else 10)
@@ -324,6 +325,8 @@ def run_ours(args):
         assert int(status.abs().sum().item()) == 0
         batch.cdf = cdf_dev
         batch.cpc = blk // chunk if args.cdf_block else 0
+        if not args.no_tables and chunk % 16 == 0 and (batch.cpc == 0 or batch.cpc % 128 == 0):
+            batch.prebuild_tables()               # coding tables once per cdf, outside the timed region like the cdf itself (turborc.c:432)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     # ---- correctness gate (untimed): device round trip, and the WHOLE packed stream + offsets byte-compared with what the
@@ -543,6 +546,7 @@ def main():
     ap.add_argument("--src", default="zipf", choices=["zipf", "bwt", "o1", "uniform"], help="synthetic source (SURVEY.md section 8d)")
     ap.add_argument("--cdf-block", type=int, default=0, help="static codecs: one cdfini table per this many bytes (0 = whole buffer)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-tables", action="store_true", help="rebuild the coding tables inside every call instead of using a prebuilt handle")
     ap.add_argument("--no-gate", action="store_true", help="skip the oracle comparison of the packed stream (device round trip only)")
     ap.add_argument("--no-extras", action="store_true", help="skip the chunk sweep and the BASELINE config 3/4 lines (extra keys of the JSON line)")
     args = ap.parse_args()

@@ -100,6 +100,24 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
                       const cdf_t *d_cdf, unsigned cdfnum, size_t chunks_per_cdf,
                       unsigned flags, void *cuda_stream);
 
+/* Prebuilt coding tables for the static codecs (TRC_ANS4S, TRC_RCS, TRC_RCS2, TRC_ANSW).  The reference harness computes its
+ * cdf once per bench() and outside the timing (turborc.c:429-433); a handle does the same for everything the kernels derive
+ * from the cdf (encoder / decoder entries, the 32 K-entry slot->symbol table): trc_tables_create_dev builds them once on the
+ * current device from `n_tables` tables laid out TRC_CDF_STRIDE apart (asynchronously on `cuda_stream`), and the *_tab calls
+ * below use them instead of rebuilding per call.  Same results as trc_enc_batch_dev / trc_dec_batch_dev byte for byte.
+ * Only the aligned geometries are served (d_in / d_out 16-byte aligned, chunk_len a multiple of 16, chunks_per_cdf 0 or a
+ * multiple of 128): anything else returns TRC_E_ARG -- use the plain calls there. */
+typedef struct trc_tables trc_tables;
+int  trc_tables_create_dev(const cdf_t *d_cdf, unsigned cdfnum, size_t n_tables, void *cuda_stream, trc_tables **out);
+void trc_tables_destroy(trc_tables *t);
+int trc_enc_batch_dev_tab(int codec, const unsigned char *d_in, size_t total_len, size_t chunk_len,
+                          const trc_tables *tables, size_t chunks_per_cdf,
+                          unsigned char *d_out, uint64_t *d_out_off,
+                          void *d_scratch, size_t scratch_bytes, void *cuda_stream);
+int trc_dec_batch_dev_tab(int codec, const unsigned char *d_in, const uint64_t *d_in_off,
+                          unsigned char *d_out, size_t total_len, size_t chunk_len,
+                          const trc_tables *tables, size_t chunks_per_cdf, unsigned flags, void *cuda_stream);
+
 /* Host-pointer flavour: copies in, runs the device path, copies the packed result and the n+1 offsets out,
  * synchronises.  Returns TRC_OK or an error; *out_len receives out_off[n]. */
 int trc_enc_batch_host(int codec, const unsigned char *in, size_t total_len, size_t chunk_len,

@@ -231,6 +231,13 @@ def test_rare_redo_paths(port, dg):
                 got, off = trc.enc_batch_host(codec, d, chunk)
                 assert np.array_equal(off, woff) and np.array_equal(got, want), (codec, chunk)
                 assert np.array_equal(trc.dec_batch_host(codec, got, off, d.size, chunk), d)
+        z = dg.zipf(300_007)                       # TRC_RCS2, lane-per-coder encoder: every call redone by the walk-back coder
+        cdf = port.cdfini(z)
+        for chunk in (1760, 4096, 304):
+            want, woff = cpu_batch(port, trc.RCS2, z, chunk, cdf, 256)
+            got, off = trc.enc_batch_host(trc.RCS2, z, chunk, cdf=cdf, cdfnum=256)
+            assert np.array_equal(off, woff) and np.array_equal(got, want), ("rcs2", chunk)
+            assert np.array_equal(trc.dec_batch_host(trc.RCS2, got, off, z.size, chunk, cdf=cdf, cdfnum=256), z)
         print("redo ok")
     ''') % (ROOT, os.path.join(ROOT, "tests"))
     env = dict(os.environ, TRC_FORCE_REDO="1")
@@ -306,3 +313,58 @@ def test_fused_encoder_many_waves(trc, port, dg):
     assert np.all(np.diff(off.astype(np.int64)) > 0) and int(off[-1]) == got.size    # ... and every call through its round trip
     back = trc.dec_batch_host(trc.RCS2, got, off, d.size, chunk, cdf=cdf, cdfnum=256)
     assert np.array_equal(back, d)
+
+
+def test_table_handles(trc, port, dg):
+    """Prebuilt coding tables (trc_tables_create_dev + *_tab calls) give the bytes of the per-call build, for one table and for
+    a table per group of chunks."""
+    import torch
+    d = dg.zipf(1_000_000 + 48, seed=3)
+    d[500_000:] = dg.bwt_shaped(d.size - 500_000)
+    t = torch.from_numpy(d).cuda()
+    for codec in (trc.RCS2, trc.RCS, trc.ANS4S, trc.ANSW):
+        for chunk, cpc in ((4096, 0), (1760, 0), (512, 128)):
+            if codec == trc.ANSW and chunk % 4:
+                continue
+            a = trc.DeviceBatch(codec, d.size, chunk, cdfnum=256, chunks_per_cdf=cpc)
+            a.cdf, status = trc.cdfini_dev(t, d.size, chunk * cpc if cpc else d.size)
+            assert int(status.abs().sum().item()) == 0
+            a.encode(t); torch.cuda.synchronize()
+            n = a.compressed_len()
+            want, woff = a.out[:n].clone(), a.off.clone()
+            a.prebuild_tables()
+            a.out.zero_(); a.off.zero_()
+            a.encode(t); torch.cuda.synchronize()
+            assert a.compressed_len() == n and torch.equal(a.off, woff) and torch.equal(a.out[:n], want), (codec, chunk, cpc)
+            assert torch.equal(a.decode(), t), (codec, chunk, cpc)
+            if codec == trc.RCS2 and cpc == 0:           # the checker's bytes, too
+                cdf = a.cdf.cpu().numpy().view(np.uint16)[:257]
+                ow, ooff = cpu_batch(port, codec, d, chunk, cdf, 256)
+                assert np.array_equal(want.cpu().numpy(), ow) and np.array_equal(woff.cpu().numpy().view(np.uint64), ooff)
+            a.drop_tables()
+
+
+def test_rcs2_ab_switches(port, dg):
+    """The A/B switches of the TRC_RCS2 kernels stay bit-exact: per-lane loads instead of TMA tiles (TRC_ENC_TMA=0), the
+    previous decoder generation (TRC_DEC3=0), the three-kernel encoder (TRC_FUSED=0).  Subprocesses: read at library load."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent('''
+        import importlib, sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        trc = importlib.import_module("turbo-range-coder_b200"); dg = importlib.import_module("turbo-range-coder_b200.datagen")
+        from oracle import cpu
+        from helpers import cpu_batch
+        port = cpu.port()
+        z = dg.zipf(2_000_003); u = dg.uniform(100_000)
+        for d in (z, u, z[:17], z[:1760], z[:1761]):
+            cdf = port.cdfini(d)
+            for chunk in (1760, 4096, 65536, 48):
+                want, woff = cpu_batch(port, trc.RCS2, d, chunk, cdf, 256)
+                got, off = trc.enc_batch_host(trc.RCS2, d, chunk, cdf=cdf, cdfnum=256)
+                assert np.array_equal(off, woff) and np.array_equal(got, want), (d.size, chunk)
+                assert np.array_equal(trc.dec_batch_host(trc.RCS2, got, off, d.size, chunk, cdf=cdf, cdfnum=256), d)
+        print("ab ok")
+    ''') % (ROOT, os.path.join(ROOT, "tests"))
+    for var in ({}, {"TRC_ENC_TMA": "0"}, {"TRC_DEC3": "0"}, {"TRC_FUSED": "0"}):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **var), timeout=900)
+        assert r.returncode == 0 and "ab ok" in r.stdout, (var, r.stdout[-2000:] + r.stderr[-2000:])

@@ -67,6 +67,13 @@ lib.trc_enc_batch_dev.restype = _i
 lib.trc_enc_batch_dev.argtypes = [_i, _vp, _sz, _sz, _vp, _u, _sz, _vp, _vp, _vp, _sz, _vp]
 lib.trc_dec_batch_dev.restype = _i
 lib.trc_dec_batch_dev.argtypes = [_i, _vp, _vp, _vp, _sz, _sz, _vp, _u, _sz, _u, _vp]
+lib.trc_tables_create_dev.restype = _i
+lib.trc_tables_create_dev.argtypes = [_vp, _u, _sz, _vp, _vp]
+lib.trc_tables_destroy.restype = None; lib.trc_tables_destroy.argtypes = [_vp]
+lib.trc_enc_batch_dev_tab.restype = _i
+lib.trc_enc_batch_dev_tab.argtypes = [_i, _vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp]
+lib.trc_dec_batch_dev_tab.restype = _i
+lib.trc_dec_batch_dev_tab.argtypes = [_i, _vp, _vp, _vp, _sz, _sz, _vp, _sz, _u, _vp]
 lib.trc_enc_batch_host.restype = _i
 lib.trc_enc_batch_host.argtypes = [_i, _vp, _sz, _sz, _vp, _u, _sz, _vp, _vp, _vp]
 lib.trc_dec_batch_host.restype = _i
@@ -214,16 +221,43 @@ class DeviceBatch:
         self.off = torch.empty(self.n + 1, dtype=torch.int64, device=self.device)
         self.dec = torch.empty(total_len + 64, dtype=torch.uint8, device=self.device)
         self.cdf = None
+        self.tables = None                    # trc_tables handle (prebuilt coding tables), see prebuild_tables()
 
     def set_cdf(self, cdf):
         c = np.ascontiguousarray(cdf, dtype=np.uint16).reshape(-1)
         self.cdf = self.torch.from_numpy(c.view(np.int16).copy()).to(self.device)
+        self.drop_tables()
+
+    def prebuild_tables(self):
+        """Build the coding tables of self.cdf once (trc_tables_create_dev); encode()/decode() then skip the per-call build."""
+        self.drop_tables()
+        n_tab = -(-self.n // self.cpc) if self.cpc else 1
+        h = ctypes.c_void_p()
+        _check(lib.trc_tables_create_dev(self.cdf.data_ptr(), self.cdfnum, n_tab, self._stream(), ctypes.byref(h)), "trc_tables_create_dev")
+        self.tables = h
+
+    def drop_tables(self):
+        if getattr(self, "tables", None):
+            self.torch.cuda.synchronize(self.device)
+            lib.trc_tables_destroy(self.tables)
+        self.tables = None
+
+    def __del__(self):
+        try:
+            self.drop_tables()
+        except Exception:      # noqa: BLE001  (interpreter shutdown)
+            pass
 
     def _stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
     def encode(self, d_in):
         """d_in: uint8 cuda tensor of total_len bytes.  Fills self.out / self.off (asynchronous)."""
+        if self.tables:
+            rc = lib.trc_enc_batch_dev_tab(self.codec, d_in.data_ptr(), self.total_len, self.chunk_len, self.tables, self.cpc,
+                                           self.out.data_ptr(), self.off.data_ptr(), self.scratch.data_ptr(), self.scratch.numel(),
+                                           self._stream())
+            return _check(rc, "trc_enc_batch_dev_tab")
         cp = self.cdf.data_ptr() if self.cdf is not None else None
         rc = lib.trc_enc_batch_dev(self.codec, d_in.data_ptr(), self.total_len, self.chunk_len, cp, self.cdfnum, self.cpc,
                                    self.out.data_ptr(), self.off.data_ptr(), self.scratch.data_ptr(), self.scratch.numel(),
@@ -234,6 +268,11 @@ class DeviceBatch:
         cp = self.cdf.data_ptr() if self.cdf is not None else None
         s = self.out if d_stream is None else d_stream
         o = self.off if d_off is None else d_off
+        if self.tables:
+            rc = lib.trc_dec_batch_dev_tab(self.codec, s.data_ptr(), o.data_ptr(), self.dec.data_ptr(), self.total_len, self.chunk_len,
+                                           self.tables, self.cpc, flags, self._stream())
+            _check(rc, "trc_dec_batch_dev_tab")
+            return self.dec[: self.total_len]
         rc = lib.trc_dec_batch_dev(self.codec, s.data_ptr(), o.data_ptr(), self.dec.data_ptr(), self.total_len, self.chunk_len,
                                    cp, self.cdfnum, self.cpc, flags, self._stream())
         _check(rc, "trc_dec_batch_dev")

@@ -36,13 +36,12 @@ constexpr int      E3_STAGES = 2;
 // {cdf, freq} of every symbol as one 8-byte entry (one LDS.64 per symbol, nothing to unpack)
 struct __align__(16) EncTab2 { uint2 e[256]; };
 
-__global__ void k_build_enctab2(const cdf_t *__restrict__ cdf, unsigned cdfnum, EncTab2 *__restrict__ t,
-                                unsigned long long *__restrict__ lb_zero, unsigned lb_n) {
-    if (lb_zero) for (unsigned k = threadIdx.x; k < lb_n; k += blockDim.x) lb_zero[k] = 0;   // look-back words + tile counter
+__global__ void k_build_enctab2(const cdf_t *__restrict__ cdf, unsigned cdfnum, EncTab2 *__restrict__ t) {   // one CTA per table
+    const cdf_t *c0 = cdf + (size_t)blockIdx.x * CDF_STRIDE;
     for (unsigned x = threadIdx.x; x < 256; x += blockDim.x) {
         uint32_t c = 0, f = 0;
-        if (x < cdfnum) { c = cdf[x]; f = (uint32_t)cdf[x + 1] - c; }
-        t->e[x] = make_uint2(c, f);
+        if (x < cdfnum) { c = c0[x]; f = (uint32_t)c0[x + 1] - c; }
+        t[blockIdx.x].e[x] = make_uint2(c, f);
     }
 }
 

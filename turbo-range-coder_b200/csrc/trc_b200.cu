@@ -189,9 +189,54 @@ static int launch_ans_enc3(bool o1, const unsigned char *d_in, const Geom &g, ui
     return TRC_OK;
 }
 
+// Prebuilt coding tables of the static codecs (include/trc_b200.h trc_tables_*): everything the kernels derive from a cdf
+// table -- built once per table set, like the harness computes cdfini once per bench() outside its timing (turborc.c:432).
+struct trc_tables {
+    int dev; unsigned cdfnum; size_t n;
+    TableSet *ts;        // rANS / RC encoder entries, decoder entries and slot->symbol LUT (static_v2.cuh, rans_wide.cuh)
+    EncTab2 *e2;         // TRC_RCS2 encoder (rcs2_v3.cuh)
+    DecTab2 *d2;         // TRC_RCS2 decoder (rcs2_v3.cuh)
+};
+
+static int enc_batch_impl(int codec, const unsigned char *d_in, size_t total_len, size_t chunk_len, const cdf_t *d_cdf, unsigned cdfnum,
+                          size_t chunks_per_cdf, const trc_tables *pre, unsigned char *d_out, uint64_t *d_out_off, void *d_scratch,
+                          size_t scratch_bytes, void *cuda_stream);
+static int dec_batch_impl(int codec, const unsigned char *d_in, const uint64_t *d_in_off, unsigned char *d_out, size_t total_len,
+                          size_t chunk_len, const cdf_t *d_cdf, unsigned cdfnum, size_t chunks_per_cdf, const trc_tables *pre,
+                          unsigned flags, void *cuda_stream);
+
 extern "C" {
 
-const char *trc_version(void) { return "trc_b200 0.1 (sm_100a)"; }
+int trc_tables_create_dev(const cdf_t *d_cdf, unsigned cdfnum, size_t n_tabs, void *cuda_stream, trc_tables **out) {
+    if (!d_cdf || !out || cdfnum == 0 || cdfnum > 256 || n_tabs == 0) return TRC_E_ARG;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    trc_tables *t = new (std::nothrow) trc_tables();
+    if (!t) return TRC_E_NOMEM;
+    t->dev = cur_dev(); t->cdfnum = cdfnum; t->n = n_tabs; t->ts = nullptr; t->e2 = nullptr; t->d2 = nullptr;
+    if (cudaMalloc((void **)&t->ts, n_tabs * sizeof(TableSet)) != cudaSuccess || cudaMalloc((void **)&t->e2, n_tabs * sizeof(EncTab2)) != cudaSuccess ||
+        cudaMalloc((void **)&t->d2, n_tabs * sizeof(DecTab2)) != cudaSuccess) {
+        snprintf(g_err, sizeof g_err, "trc_tables_create_dev: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(t->ts); cudaFree(t->e2); cudaFree(t->d2); delete t; return TRC_E_NOMEM;
+    }
+    k_build_tables<<<dim3((unsigned)n_tabs, 1 + LUT_PARTS), 1024, 0, st>>>(d_cdf, cdfnum, t->ts, 1);
+    k_build_enctab2<<<(unsigned)n_tabs, 256, 0, st>>>(d_cdf, cdfnum, t->e2);
+    k_build_dectab2<<<dim3((unsigned)n_tabs, 1 + LUT_PARTS), 1024, 0, st>>>(d_cdf, cdfnum, t->d2);
+    g_launches += 3;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { snprintf(g_err, sizeof g_err, "trc_tables_create_dev: %s", cudaGetErrorString(e)); cudaFree(t->ts); cudaFree(t->e2); cudaFree(t->d2); delete t; return TRC_E_CUDA; }
+    *out = t;
+    return TRC_OK;
+}
+void trc_tables_destroy(trc_tables *t) {
+    if (!t) return;
+    int prev = 0; cudaGetDevice(&prev);
+    if (prev != t->dev) cudaSetDevice(t->dev);
+    cudaFree(t->ts); cudaFree(t->e2); cudaFree(t->d2);
+    if (prev != t->dev) cudaSetDevice(prev);
+    delete t;
+}
+
+const char *trc_version(void) { return "trc_b200 0.2 (sm_100a)"; }
 const char *trc_last_error(void) { return g_err; }
 int trc_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 int trc_set_device(int dev) { g_dev = dev; CK(cudaSetDevice(dev)); return TRC_OK; }
@@ -250,10 +295,39 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
                       const cdf_t *d_cdf, unsigned cdfnum, size_t chunks_per_cdf,
                       unsigned char *d_out, uint64_t *d_out_off,
                       void *d_scratch, size_t scratch_bytes, void *cuda_stream) {
+    return enc_batch_impl(codec, d_in, total_len, chunk_len, d_cdf, cdfnum, chunks_per_cdf, nullptr, d_out, d_out_off, d_scratch, scratch_bytes, cuda_stream);
+}
+int trc_enc_batch_dev_tab(int codec, const unsigned char *d_in, size_t total_len, size_t chunk_len,
+                          const trc_tables *tables, size_t chunks_per_cdf,
+                          unsigned char *d_out, uint64_t *d_out_off,
+                          void *d_scratch, size_t scratch_bytes, void *cuda_stream) {
+    if (!tables || !codec_static(codec)) return TRC_E_ARG;
+    if (tables->n < n_tables(trc_num_chunks(total_len, chunk_len), chunks_per_cdf) || tables->dev != cur_dev()) return TRC_E_ARG;
+    return enc_batch_impl(codec, d_in, total_len, chunk_len, nullptr, tables->cdfnum, chunks_per_cdf, tables, d_out, d_out_off, d_scratch, scratch_bytes, cuda_stream);
+}
+int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in_off,
+                      unsigned char *d_out, size_t total_len, size_t chunk_len,
+                      const cdf_t *d_cdf, unsigned cdfnum, size_t chunks_per_cdf,
+                      unsigned flags, void *cuda_stream) {
+    return dec_batch_impl(codec, d_in, d_in_off, d_out, total_len, chunk_len, d_cdf, cdfnum, chunks_per_cdf, nullptr, flags, cuda_stream);
+}
+int trc_dec_batch_dev_tab(int codec, const unsigned char *d_in, const uint64_t *d_in_off,
+                          unsigned char *d_out, size_t total_len, size_t chunk_len,
+                          const trc_tables *tables, size_t chunks_per_cdf, unsigned flags, void *cuda_stream) {
+    if (!tables || !codec_static(codec)) return TRC_E_ARG;
+    if (tables->n < n_tables(trc_num_chunks(total_len, chunk_len), chunks_per_cdf) || tables->dev != cur_dev()) return TRC_E_ARG;
+    return dec_batch_impl(codec, d_in, d_in_off, d_out, total_len, chunk_len, nullptr, tables->cdfnum, chunks_per_cdf, tables, flags, cuda_stream);
+}
+
+}  // extern "C"
+
+static int enc_batch_impl(int codec, const unsigned char *d_in, size_t total_len, size_t chunk_len, const cdf_t *d_cdf, unsigned cdfnum,
+                          size_t chunks_per_cdf, const trc_tables *pre, unsigned char *d_out, uint64_t *d_out_off, void *d_scratch,
+                          size_t scratch_bytes, void *cuda_stream) {
     Plan p; int rc = make_plan(codec, total_len, chunk_len, p);
     if (rc != TRC_OK) return rc;
     if (!d_in || !d_out || !d_out_off || !d_scratch) return TRC_E_ARG;
-    if (codec_static(codec) && (!d_cdf || cdfnum == 0 || cdfnum > 256)) return TRC_E_ARG;
+    if (codec_static(codec) && ((!d_cdf && !pre) || cdfnum == 0 || cdfnum > 256)) return TRC_E_ARG;
     uint8_t *sc = (uint8_t *)al256((size_t)d_scratch);
     if ((size_t)(sc - (uint8_t *)d_scratch) + p.total > scratch_bytes) return TRC_E_NOMEM;
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -266,15 +340,15 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     g_prof_n = 0;
     const bool v2 = codec_static(codec) && v2_ok(d_in, chunk_len, chunks_per_cdf);
     if (codec == ANSW && !(((uintptr_t)d_in & 3) == 0 && (chunks_per_cdf == 0 || chunks_per_cdf % V2_NT == 0))) return TRC_E_ARG;
-    TableSet *tabs = (TableSet *)(sc + p.off_tabs);
+    TableSet *tabs = pre ? pre->ts : (TableSet *)(sc + p.off_tabs);
     const bool fused = g_fused && codec == RCS2 && v2 && chunks_per_cdf == 0;
     if (fused) {                 // TRC_RCS2, one table: coder + offsets + layout in ONE kernel (rcs2_v3.cuh)
         const size_t n_full = total_len / chunk_len;                        // the tensor map covers full chunks only (see rcs2_v3.cuh)
-        EncTab2 *t2 = (EncTab2 *)tabs;
+        EncTab2 *t2 = pre ? pre->e2 : (EncTab2 *)tabs;
         unsigned cpcta = 0, ctas = 0;
         e3_shape(g.n_calls, cpcta, ctas);
-        k_build_enctab2<<<1, 256, 0, st>>>(d_cdf, cdfnum, t2, (unsigned long long *)(sc + p.off_lb), ctas + 1);
-        CK_LAUNCH();
+        CK(cudaMemsetAsync(sc + p.off_lb, 0, (size_t)(ctas + 1) * 8, st));   // look-back words + tile counter
+        if (!pre) { k_build_enctab2<<<1, 256, 0, st>>>(d_cdf, cdfnum, t2); CK_LAUNCH(); }
         prof_mark(st);
         const unsigned nt = (2 * cpcta + 31) & ~31u;
         const bool tma = g_enc_tma && n_full && tmap_encode() && n_full < (1ull << 31);
@@ -296,10 +370,11 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
         prof_mark(st); prof_mark(st); prof_mark(st);
         return TRC_OK;
     }
-    if (v2 || codec == ANSW) {   // symbol tables once per launch
+    if ((v2 || codec == ANSW) && !pre) {   // symbol tables once per launch
         k_build_tables<<<dim3((unsigned)n_tables(g.n_calls, chunks_per_cdf), 1), 256, 0, st>>>(d_cdf, cdfnum, tabs, 0);
         CK_LAUNCH();
     }
+    if (pre && !v2 && codec != ANSW) return TRC_E_ARG;                  // prebuilt tables serve the aligned (throughput) kernels only
     const unsigned v2nt = v2_shape(g.n_calls, chunks_per_cdf);
     prof_mark(st);
     switch (codec) {
@@ -350,14 +425,13 @@ int trc_enc_batch_dev(int codec, const unsigned char *d_in, size_t total_len, si
     return TRC_OK;
 }
 
-int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in_off,
-                      unsigned char *d_out, size_t total_len, size_t chunk_len,
-                      const cdf_t *d_cdf, unsigned cdfnum, size_t chunks_per_cdf,
-                      unsigned flags, void *cuda_stream) {
+static int dec_batch_impl(int codec, const unsigned char *d_in, const uint64_t *d_in_off, unsigned char *d_out, size_t total_len,
+                          size_t chunk_len, const cdf_t *d_cdf, unsigned cdfnum, size_t chunks_per_cdf, const trc_tables *pre,
+                          unsigned flags, void *cuda_stream) {
     Plan p; int rc = make_plan(codec, total_len, chunk_len, p);
     if (rc != TRC_OK) return rc;
     if (!d_in || !d_in_off || !d_out) return TRC_E_ARG;
-    if (codec_static(codec) && (!d_cdf || cdfnum == 0 || cdfnum > 256)) return TRC_E_ARG;
+    if (codec_static(codec) && ((!d_cdf && !pre) || cdfnum == 0 || cdfnum > 256)) return TRC_E_ARG;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     Geom g = p.g; g.upc = 1; g.n_units = g.n_calls;     // decoders work per call
     auto blocks = [](size_t n, int nt) { return (unsigned)((n + nt - 1) / nt); };
@@ -366,29 +440,33 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
     static const int g_dec3 = getenv("TRC_DEC3") ? atoi(getenv("TRC_DEC3")) : 1;     // 0: previous generation of the TRC_RCS2 decoder (A/B runs)
     if (codec == RCS2 && g_dec3 && v2_ok(d_out, chunk_len, chunks_per_cdf) && ((uintptr_t)d_in & 15) == 0) {
         rc = dev_attrs(); if (rc) return rc;
-        rc = pool_keep(); if (rc) return rc;
-        DecTab2 *t2 = nullptr;
-        const size_t nt = n_tables(g.n_calls, chunks_per_cdf);
-        CK(cudaMallocAsync((void **)&t2, nt * sizeof(DecTab2), st));
-        k_build_dectab2<<<dim3((unsigned)nt, 1 + LUT_PARTS), 1024, 0, st>>>(d_cdf, cdfnum, t2);
-        g_launches++;
+        DecTab2 *t2 = pre ? pre->d2 : nullptr;
+        if (!pre) {
+            rc = pool_keep(); if (rc) return rc;
+            const size_t nt = n_tables(g.n_calls, chunks_per_cdf);
+            CK(cudaMallocAsync((void **)&t2, nt * sizeof(DecTab2), st));
+            k_build_dectab2<<<dim3((unsigned)nt, 1 + LUT_PARTS), 1024, 0, st>>>(d_cdf, cdfnum, t2);
+            g_launches++;
+        }
         prof_mark(st);
         unsigned cpcta, ctas; lpc_shape(g.n_calls, chunks_per_cdf, cpcta, ctas);
         const unsigned nt2 = (2 * cpcta + 31) & ~31u;
         k_rcs2_dec3<<<ctas, nt2, D3_SMEM, st>>>(d_in, d_in_off, d_out, g, g.n_calls, t2, cdfnum, chunks_per_cdf, cpcta);
         g_launches++; prof_mark(st);
         cudaError_t e = cudaPeekAtLastError();
-        cudaFreeAsync(t2, st);
+        if (!pre) cudaFreeAsync(t2, st);
         CK(e);
         return TRC_OK;
     }
     if (codec == ANSW || (codec_static(codec) && v2_ok(d_out, chunk_len, chunks_per_cdf) && ((uintptr_t)d_in & 15) == 0)) {
-        rc = pool_keep(); if (rc) return rc;
-        TableSet *tabs = nullptr;
-        const size_t nt = n_tables(g.n_calls, chunks_per_cdf);
-        CK(cudaMallocAsync((void **)&tabs, nt * sizeof(TableSet), st));
-        k_build_tables<<<dim3((unsigned)nt, 1 + LUT_PARTS), 1024, 0, st>>>(d_cdf, cdfnum, tabs, 1);
-        g_launches++;
+        TableSet *tabs = pre ? pre->ts : nullptr;
+        if (!pre) {
+            rc = pool_keep(); if (rc) return rc;
+            const size_t nt = n_tables(g.n_calls, chunks_per_cdf);
+            CK(cudaMallocAsync((void **)&tabs, nt * sizeof(TableSet), st));
+            k_build_tables<<<dim3((unsigned)nt, 1 + LUT_PARTS), 1024, 0, st>>>(d_cdf, cdfnum, tabs, 1);
+            g_launches++;
+        }
         prof_mark(st);
         if (codec == ANSW) k_answ_dec<<<blocks(g.n_calls, ANSW_WPB), ANSW_WPB * 32, 0, st>>>(d_in, d_in_off, d_out, g, tabs, chunks_per_cdf);
         else if (codec == ANS4S) { const unsigned v2nt = v2_shape(g.n_calls, chunks_per_cdf);
@@ -403,10 +481,11 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
                k_rcs2_dec_lpc<<<ctas, nt, RING_W * nt * sizeof(uint32_t), st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf, cpcta); }
         g_launches++; prof_mark(st);
         cudaError_t e = cudaPeekAtLastError();
-        cudaFreeAsync(tabs, st);
+        if (!pre) cudaFreeAsync(tabs, st);
         CK(e);
         return TRC_OK;
     }
+    if (pre) return TRC_E_ARG;                                          // prebuilt tables serve the aligned (throughput) kernels only
     prof_mark(st);
     switch (codec) {
     case ANS4S: k_rans_static_dec<<<blocks(g.n_calls, RANS_SD_NT), RANS_SD_NT, 0, st>>>(d_in, d_in_off, d_out, g, d_cdf, cdfnum, chunks_per_cdf, flags); break;
@@ -442,6 +521,8 @@ int trc_dec_batch_dev(int codec, const unsigned char *d_in, const uint64_t *d_in
     CK_LAUNCH(); prof_mark(st);
     return TRC_OK;
 }
+
+extern "C" {
 
 int trc_cdfini_batch_dev(const unsigned char *d_in, size_t total_len, size_t chunk_len,
                          cdf_t *d_cdf, unsigned cdfnum, int *d_status, void *cuda_stream) {
