@@ -134,6 +134,19 @@ int trc_dec_batch_host(int codec, const unsigned char *in, const uint64_t *in_of
 int trc_cdfini_batch_dev(const unsigned char *d_in, size_t total_len, size_t chunk_len,
                          cdf_t *d_cdf, unsigned cdfnum, int *d_status, void *cuda_stream);
 
+/* Several GPUs from ONE process (the reference harness calls from a single thread, turborc.c:420).
+ * The batch is cut into contiguous shards of whole chunks (whole table groups when chunks_per_cdf != 0), shard r on device
+ * devs[r], one host thread per device.  Encode: the devices code independently, the shard sizes are exchanged once, every
+ * device downloads its packed stream to its final place in `out`: the result (bytes, offsets, length) is identical to
+ * trc_enc_batch_host on one device.  Decode: the chunk directory in_off tells each device which slice of the stream to
+ * fetch; every device uploads only its slice and downloads only its part of the output.  devs must be distinct. */
+int trc_enc_batch_host_multi(int codec, const int *devs, int n_dev, const unsigned char *in, size_t total_len, size_t chunk_len,
+                             const cdf_t *cdf, unsigned cdfnum, size_t chunks_per_cdf,
+                             unsigned char *out, uint64_t *out_off, size_t *out_len);
+int trc_dec_batch_host_multi(int codec, const int *devs, int n_dev, const unsigned char *in, const uint64_t *in_off,
+                             unsigned char *out, size_t total_len, size_t chunk_len,
+                             const cdf_t *cdf, unsigned cdfnum, size_t chunks_per_cdf, unsigned flags);
+
 /* ------------------------------------------------------------------------------------------------------
  * Self-describing container.  The reference's codec calls carry no lengths, tables
  * or cdfnum -- bench() keeps them on the side (turborc.c:423-433) and file mode wraps every block in a
@@ -165,7 +178,10 @@ int trc_ipc_export(void *p, unsigned char *handle64);
 int trc_ipc_open(const unsigned char *handle64, void **p);
 int trc_ipc_close(void *p);
 int trc_memcpy_dev(void *dst, const void *src, size_t bytes, void *cuda_stream);
-int trc_push_dev(void *dst, const void *src, const uint64_t *d_len, size_t fixed_len, uint64_t *dst_len, void *cuda_stream);
+int trc_push_dev(void *dst, const void *src, const uint64_t *d_len, size_t fixed_len, size_t cap, uint64_t *dst_len,
+                 uint64_t *dst_flag, uint64_t seq, unsigned int *d_counter, const uint64_t *ack, uint64_t ack_need, void *cuda_stream);
+int trc_ack_dev(uint64_t *ack, uint64_t seq, void *cuda_stream);
+int trc_wait_flags_dev(const uint64_t *flags, const uint64_t *lens, unsigned n, uint64_t seq, unsigned int *d_status, void *cuda_stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * Drop-in layer: the reference's names, signatures and return values.

@@ -1,7 +1,7 @@
 import sys, os, importlib, time, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 trc = importlib.import_module("turbo-range-coder_b200"); dg = importlib.import_module("turbo-range-coder_b200.datagen")
-n=100_000_000; chunk=4096
+n=100_000_000; chunk=int(sys.argv[1]) if len(sys.argv) > 1 else 1760
 data = dg.zipf(n)
 h_in = torch.from_numpy(data).pin_memory().numpy()
 h_out = torch.empty(int(trc.lib.trc_enc_bound(n, chunk)), dtype=torch.uint8).pin_memory().numpy()

@@ -156,6 +156,42 @@ def dec_batch_host(codec, stream, off, total_len, chunk_len, cdf=None, cdfnum=0,
     return out
 
 
+lib.trc_enc_batch_host_multi.restype = _i
+lib.trc_enc_batch_host_multi.argtypes = [_i, _vp, _i, _vp, _sz, _sz, _vp, _u, _sz, _vp, _vp, _vp]
+lib.trc_dec_batch_host_multi.restype = _i
+lib.trc_dec_batch_host_multi.argtypes = [_i, _vp, _i, _vp, _vp, _vp, _sz, _sz, _vp, _u, _sz, _u]
+
+
+def enc_batch_host_multi(codec, devs, data, chunk_len, cdf=None, cdfnum=0, chunks_per_cdf=0, out=None, off=None):
+    """enc_batch_host with the chunks sharded over the GPUs `devs` (one process, one host thread per device)."""
+    data = _u8(data)
+    n = num_chunks(data.size, chunk_len)
+    if out is None:
+        out = np.empty(int(lib.trc_enc_bound(data.size, chunk_len)), np.uint8)
+    if off is None:
+        off = np.empty(n + 1, np.uint64)
+    keep, cp = _cdfarg(cdf)
+    dv = (ctypes.c_int * len(devs))(*devs)
+    olen = ctypes.c_size_t(0)
+    rc = lib.trc_enc_batch_host_multi(codec, dv, len(devs), data.ctypes.data, data.size, chunk_len, cp, cdfnum, chunks_per_cdf,
+                                      out.ctypes.data, off.ctypes.data, ctypes.addressof(olen))
+    _check(rc, "trc_enc_batch_host_multi")
+    return out[:olen.value], off
+
+
+def dec_batch_host_multi(codec, devs, stream, off, total_len, chunk_len, cdf=None, cdfnum=0, chunks_per_cdf=0, flags=0, out=None):
+    stream = _u8(stream)
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    if out is None:
+        out = np.empty(total_len, np.uint8)
+    keep, cp = _cdfarg(cdf)
+    dv = (ctypes.c_int * len(devs))(*devs)
+    rc = lib.trc_dec_batch_host_multi(codec, dv, len(devs), stream.ctypes.data, off.ctypes.data, out.ctypes.data, total_len, chunk_len,
+                                      cp, cdfnum, chunks_per_cdf, flags)
+    _check(rc, "trc_dec_batch_host_multi")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------
 # self-describing container (include/trc_b200.h): tables computed on the GPU, directory + payload in one buffer
 # ----------------------------------------------------------------------------------------------------------
@@ -236,11 +272,16 @@ class DeviceBatch:
         _check(lib.trc_tables_create_dev(self.cdf.data_ptr(), self.cdfnum, n_tab, self._stream(), ctypes.byref(h)), "trc_tables_create_dev")
         self.tables = h
 
+    def borrow_tables(self, other):
+        """Use the prebuilt tables of another DeviceBatch on the same device and cdf (not owned: `other` must outlive this)."""
+        self.drop_tables()
+        self.tables, self._borrowed = other.tables, True
+
     def drop_tables(self):
-        if getattr(self, "tables", None):
+        if getattr(self, "tables", None) and not getattr(self, "_borrowed", False):
             self.torch.cuda.synchronize(self.device)
             lib.trc_tables_destroy(self.tables)
-        self.tables = None
+        self.tables, self._borrowed = None, False
 
     def __del__(self):
         try:

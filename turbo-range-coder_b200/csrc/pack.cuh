@@ -106,12 +106,23 @@ __global__ void k_publish_u64(const uint64_t *__restrict__ src, uint64_t *__rest
 // ---- push: device-driven copy of a packed stream into (peer) memory ------------------------------------------
 // The byte count lives in device memory (it is the encoder's out_off[n]), so no host round trip is needed to size
 // the transfer.  dst may be a CUDA-IPC mapping of another GPU's buffer: the 128-bit stores then travel over
-// NVLink/NVSwitch.  Thread 0 publishes the length next to the payload.
+// NVLink/NVSwitch.  Completion protocol (a consumer on the destination GPU must never see a partial stream):
+// every CTA fences its stores system-wide and bumps a counter in LOCAL memory; the CTA that finds the counter complete
+// publishes the length, fences again, and only then writes the sequence number into the destination's flag word.  The
+// consumer (k_wait_flags on the destination) spins on the flag with volatile loads: flag >= seq  =>  length and payload of
+// push `seq` have landed.  A stream longer than the slot is not copied beyond `cap`: the published length keeps the TRUE size
+// with its top bit set, which the consumer reports as an overflow.
+constexpr unsigned long long PUSH_OVERFLOW = 1ull << 63;
 __global__ void __launch_bounds__(256)
-k_push(uint4 *__restrict__ dst, const uint4 *__restrict__ src, const uint64_t *__restrict__ d_len, size_t fixed_len,
-       uint64_t *__restrict__ dst_len) {
+k_push(uint4 *__restrict__ dst, const uint4 *__restrict__ src, const uint64_t *__restrict__ d_len, size_t fixed_len, size_t cap,
+       uint64_t *__restrict__ dst_len, volatile uint64_t *__restrict__ dst_flag, uint64_t seq, unsigned int *__restrict__ counter,
+       const volatile uint64_t *__restrict__ ack, uint64_t ack_need) {
+    // back-pressure: the slot may be overwritten only after the consumer acknowledged the push that used it last
+    if (ack && threadIdx.x == 0) while (*ack < ack_need) __nanosleep(128);
+    if (ack) __syncthreads();
     const uint64_t len = d_len ? *d_len : (uint64_t)fixed_len;
-    const size_t nv = (size_t)((len + 15) >> 4), stride = (size_t)gridDim.x * blockDim.x;
+    const uint64_t clen = cap && len > cap ? cap : len;
+    const size_t nv = (size_t)((clen + 15) >> 4), stride = (size_t)gridDim.x * blockDim.x;
     // four 16-byte chunks in flight per thread: the kernel runs on a few CTAs next to the decoder, so the bandwidth over
     // NVLink has to come from memory-level parallelism per thread, not from thread count
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -120,8 +131,32 @@ k_push(uint4 *__restrict__ dst, const uint4 *__restrict__ src, const uint64_t *_
         dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
     }
     for (; i < nv; i += stride) dst[i] = src[i];
-    if (dst_len && blockIdx.x == 0 && threadIdx.x == 0) *dst_len = len;
+    __threadfence_system();                                           // this thread's stores are visible system-wide ...
+    __syncthreads();                                                  // ... for every thread of the CTA
+    if (threadIdx.x == 0) {
+        const unsigned done = counter ? atomicAdd(counter, 1u) : gridDim.x - 1;
+        if (done == gridDim.x - 1) {                                  // (no counter: no flag either, every CTA just repeats the length)
+            if (counter) *counter = 0;                                // ready for the next push (pushes are stream-ordered)
+            if (dst_len) *dst_len = len == clen ? len : (len | PUSH_OVERFLOW);
+            __threadfence_system();
+            if (dst_flag) *dst_flag = seq;                            // release: everything above is visible before the flag
+        }
+    }
 }
+
+// consumer side of the protocol: returns (kernel completes) once every flag[r] >= seq.  status[0] |= 1 when a published
+// length carries the overflow bit.  One thread per flag.
+__global__ void k_wait_flags(const volatile uint64_t *__restrict__ flags, const volatile uint64_t *__restrict__ lens, unsigned n, uint64_t seq,
+                             unsigned int *__restrict__ status) {
+    const unsigned r = threadIdx.x;                                   // one CTA, one thread per producer
+    if (r < n) {
+        while (flags[r] < seq) __nanosleep(64);
+        __threadfence_system();                                       // acquire: payload / length reads after this see the pushed data
+        if (status && lens && (lens[r] & PUSH_OVERFLOW)) atomicOr(status, 1u);
+    }
+}
+// consumer is done with the slot set of push `seq`: producers may reuse it (k_push spins on this word over the peer mapping)
+__global__ void k_ack(volatile uint64_t *__restrict__ ack, uint64_t seq) { if (threadIdx.x == 0) { __threadfence_system(); *ack = seq; } }
 
 // ---- pack ----------------------------------------------------------------------------------------------
 // grid = (n_units, segments); each CTA moves one `seg`-byte segment of one unit's output.

@@ -557,149 +557,9 @@ k_rcs2_enc_lpc(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const Tab
     meta[j] = m;
 }
 
-// =========================================================================================================
-// TRC_RCS2 encoder with the layout pass FUSED in: the same lane-per-coder body as k_rcs2_enc_lpc, then -- instead of leaving
-// lengths for k_resolve / k_scan / k_pack -- the CTA scans the lengths of its calls, obtains its base offset from the
-// CTAs before it with a decoupled look-back (one 64-bit word per CTA: flag | value, zeroed by k_build_tables), writes
-// out_off[] and copies its calls' pieces from the slots (still hot in L2) to their final place, a warp per call.
-// Removes two kernels, their launch gaps and one full pass over HBM from the encode side.  Used when one table serves the
-// whole batch (cpc == 0); per-block tables and ragged geometries keep the three-kernel path.
-// =========================================================================================================
+// look-back words of the fused encoder (rcs2_v3.cuh k_rcs2_enc3): flag in the top two bits, running byte count below
 constexpr int LB_U = 24;                                        // words in flight per lane in the layout epilogue
 constexpr unsigned long long LB_AGG = 1ull << 62, LB_INC = 2ull << 62, LB_VAL = LB_AGG - 1;
-
-__global__ void __launch_bounds__(LPC_MAX_NT, 1)
-k_rcs2_enc_fused(const uint8_t *__restrict__ in, Geom g, size_t n_calls, const TableSet *__restrict__ ts,
-                 uint8_t *__restrict__ slots, size_t slot_stride, unsigned calls_per_cta,
-                 volatile unsigned long long *__restrict__ lb, uint64_t *__restrict__ out_off, uint8_t *__restrict__ out) {
-    __shared__ __align__(16) uint32_t ctab[256];
-    __shared__ uint64_t bar;
-    __shared__ uint32_t s_len[LPC_MAX_NT / 2], s_alen[LPC_MAX_NT / 2], s_boff[LPC_MAX_NT / 2], s_blen[LPC_MAX_NT / 2], s_excl[LPC_MAX_NT / 2];
-    constexpr int NW = LPC_MAX_NT / 32;                        // warp sums; [NW] = the CTA aggregate
-    __shared__ uint32_t s_wsum[NW + 1];
-    __shared__ unsigned long long s_base;
-    // tile index in ARRIVAL order (lb[gridDim.x] is a counter): a CTA only ever waits for tiles that already run, whatever
-    // order the hardware starts CTAs in -- the look-back cannot deadlock on grids of more than one wave
-    __shared__ unsigned s_tile;
-    if (threadIdx.x == 0) {
-        s_tile = (unsigned)atomicAdd((unsigned long long *)(lb + gridDim.x), 1ull);
-        tma_fetch(ctab, ts->ctab, sizeof ctab, &bar);
-    }
-    __syncthreads();
-    tma_wait(&bar);
-    const unsigned bid = s_tile;
-    const size_t j0 = (size_t)bid * calls_per_cta, j = j0 + (threadIdx.x >> 1);
-    const unsigned c = threadIdx.x & 1, r = threadIdx.x >> 1;
-    const bool live = j < n_calls && r < calls_per_cta;
-    size_t start = 0, n = 0;
-    if (live) call_span(g, j, start, n);
-    const uint8_t *ip = in + start;
-    uint8_t *slot = slots + (live ? j : 0) * slot_stride;
-    const int64_t thr = rc_thr(n);
-    const bool tiny = n < 4;
-    const uint32_t b1ref = tiny ? 4 : 4 + (uint32_t)(((n - 4) * 37) / 64);           // rccdf.c:126
-    const uint32_t b1 = (b1ref + 64 + 15) & ~15u;
-    RcE32 e; e.init(slot + (c ? b1 : 4));
-    bool raw = tiny || !live;
-    const size_t nb = n & ~(size_t)15;
-    uint4 cur = (nb && !raw) ? ldg128(ip) : make_uint4(0, 0, 0, 0);
-    uint4 nxt = (nb >= 32 && !raw) ? ldg128(ip + 16) : cur;
-    for (size_t i = 0; i < nb && !raw; i += 16) {
-        const uint4 nxt2 = i + 48 <= nb ? ldg128(ip + i + 32) : nxt;
-        const uint32_t w[4] = { cur.x >> (8 * c), cur.y >> (8 * c), cur.z >> (8 * c), cur.w >> (8 * c) };
-        uint32_t tt[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) tt[k] = ctab[(w[k >> 1] >> (16 * (k & 1))) & 0xff];
-#pragma unroll
-        for (int k = 0; k < 8; k++) e.encode(tt[k] & 0xffffu, tt[k] >> 16);
-        raw = c ? (int64_t)b1ref + e.bytes() >= thr : 4 + e.bytes() >= b1ref;       // own half of OVERFLOWI
-        cur = nxt; nxt = nxt2;
-    }
-    for (size_t i = nb + c; i < (n & ~(size_t)1) && !raw; i += 2) {
-        uint32_t tk = ctab[ip[i]]; e.encode(tk & 0xffffu, tk >> 16);
-        raw = c ? (int64_t)b1ref + e.bytes() >= thr : 4 + e.bytes() >= b1ref;
-    }
-    raw = __shfl_xor_sync(0xffffffffu, (int)raw, 1) || raw;
-    if (!raw) {
-        if (c == 0 && (n & 1)) { uint32_t tk = ctab[ip[n - 1]]; e.encode(tk & 0xffffu, tk >> 16); }
-        e.flush();
-    }
-    const uint32_t mypos = e.bytes(), other = __shfl_xor_sync(0xffffffffu, mypos, 1);
-    const uint32_t rare = e.rare | __shfl_xor_sync(0xffffffffu, e.rare, 1);
-    if (c == 0 && r < LPC_MAX_NT / 2) {
-        UnitMeta m; m.a_off = 0; m.a_len = 0; m.b_off = b1; m.b_len = 0; m.len = 0; m.flags = 0;
-        if (live) {
-            const uint32_t p0 = mypos, p1 = other;
-            if (!raw) { *(uint32_t *)slot = p0; if ((int64_t)(4 + p0 + p1) >= thr) raw = true; }   // rccdf.c:141-142
-            if (rare && !raw) rc_static_enc_call<2, true>(ip, n, ctab, nullptr, slot, m);          // wrapped pending word: walk-back coder
-            else { m.a_len = raw ? 0 : 4 + p0; m.b_len = raw ? 0 : p1; m.len = raw ? (uint32_t)n : 4 + p0 + p1; m.flags = raw ? UM_RAW : 0; }
-        }
-        s_len[r] = m.len; s_alen[r] = (m.flags & UM_RAW) ? 0xffffffffu : m.a_len; s_boff[r] = m.b_off; s_blen[r] = m.b_len;
-    }
-    __syncthreads();
-    // ---- exclusive scan of the call lengths of this CTA (calls_per_cta <= 256: thread t scans entry t)
-    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t v = threadIdx.x < calls_per_cta ? s_len[threadIdx.x] : 0, inc = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if ((int)lane >= d) inc += t; }
-    if (lane == 31) s_wsum[wid] = inc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (unsigned k = 0; k < (blockDim.x + 31) / 32; k++) { const uint32_t t = s_wsum[k]; s_wsum[k] = run; run += t; }
-        s_wsum[NW] = run;
-    }
-    __syncthreads();
-    if (threadIdx.x < calls_per_cta) s_excl[threadIdx.x] = s_wsum[wid] + inc - v;
-    // ---- decoupled look-back for the CTA's base offset
-    if (wid == 0) {
-        const unsigned long long agg = s_wsum[NW];
-        if (lane == 0) { lb[bid] = (bid == 0 ? LB_INC : LB_AGG) | agg; __threadfence(); }
-        unsigned long long base = 0;
-        if (bid) {
-            long long idx = (long long)bid - 1;
-            for (;;) {
-                const long long k = idx - lane;
-                unsigned long long st = LB_INC;                   // before CTA 0: inclusive prefix 0
-                if (k >= 0) do { st = lb[k]; } while ((st >> 62) == 0);
-                const unsigned incl = __ballot_sync(0xffffffffu, (st >> 62) == 2);
-                const unsigned first = incl ? __ffs((int)incl) - 1 : 32;                 // nearest predecessor holding an inclusive prefix
-                unsigned long long val = lane <= first ? (st & LB_VAL) : 0;
-#pragma unroll
-                for (int d = 16; d; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-                base += val;
-                if (incl) break;
-                idx -= 32;
-            }
-            if (lane == 0) { lb[bid] = LB_INC | (base + agg); __threadfence(); }
-        }
-        if (lane == 0) s_base = base;
-    }
-    __syncthreads();
-    const unsigned long long base = s_base;
-    if (threadIdx.x < calls_per_cta && j0 + threadIdx.x < n_calls) out_off[j0 + threadIdx.x] = base + s_excl[threadIdx.x];
-    if (threadIdx.x == 0 && j0 + calls_per_cta >= n_calls) out_off[n_calls] = base + s_wsum[NW];
-    // ---- layout: a warp per call, pieces from the slot (or the input, for a raw call) to their final place
-    for (unsigned q = wid; q < calls_per_cta && j0 + q < n_calls; q += blockDim.x >> 5) {
-        uint8_t *dst = out + base + s_excl[q];
-        const uint8_t *sl = slots + (j0 + q) * slot_stride;
-        if (s_alen[q] == 0xffffffffu) { size_t st2, n2; call_span(g, j0 + q, st2, n2); group_copy4(dst, in + st2, n2, lane, 32); }
-        else if (((uintptr_t)dst & 3) == 0) {
-            // both pieces are whole words and start word-aligned in the slot: word-wise, coalesced, 16 loads in flight per lane
-            // (only ~11 warps per SM run this epilogue, so the memory-level parallelism has to come from each lane)
-            const uint32_t *pa = (const uint32_t *)sl, *pb = (const uint32_t *)(sl + s_boff[q]);
-            const uint32_t wa = s_alen[q] >> 2, W = wa + (s_blen[q] >> 2);
-            uint32_t *d = (uint32_t *)dst;
-            for (uint32_t w0 = 0; w0 < W; w0 += LB_U * 32) {
-                uint32_t vv[LB_U];
-#pragma unroll
-                for (int k = 0; k < LB_U; k++) { const uint32_t w = w0 + k * 32 + lane; vv[k] = w < wa ? pa[w] : (w < W ? pb[w - wa] : 0u); }
-#pragma unroll
-                for (int k = 0; k < LB_U; k++) { const uint32_t w = w0 + k * 32 + lane; if (w < W) d[w] = vv[k]; }
-            }
-        } else { group_copy(dst, sl, s_alen[q], lane, 32); if (s_blen[q]) group_copy(dst + s_alen[q], sl + s_boff[q], s_blen[q], lane, 32); }
-    }
-}
 
 __global__ void __launch_bounds__(LPC_MAX_NT, 1)
 k_rcs2_dec_lpc(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint8_t *__restrict__ out, Geom g,

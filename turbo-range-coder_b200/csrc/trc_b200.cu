@@ -16,7 +16,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
+#include <string>
 #include <vector>
 #include <chrono>
 
@@ -26,8 +29,7 @@ static thread_local char g_err[256] = "";
 static int g_dev = 0;
 static const int g_force_redo = getenv("TRC_FORCE_REDO") ? 1 : 0;   // test hook: exercise the rare walk-back redo paths
 static const int g_fused = getenv("TRC_FUSED") ? atoi(getenv("TRC_FUSED")) : 1;             // 0: coder, scan and pack as separate kernels (A/B runs)
-static const int g_adapt_v3 = getenv("TRC_ADAPT_V3") ? atoi(getenv("TRC_ADAPT_V3")) : 1;   // 0: previous generation of the adaptive byte rANS kernels (A/B runs)
-static unsigned long long g_launches = 0;       // kernels launched by this library (bench.py reports the delta)
+static std::atomic<unsigned long long> g_launches{0};   // kernels launched by this library (bench.py reports the delta)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     snprintf(g_err, sizeof g_err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); return TRC_E_CUDA; } } while (0)
@@ -36,11 +38,13 @@ static unsigned long long g_launches = 0;       // kernels launched by this libr
 // Optional per-kernel timing of the batch calls (bench.py's roofline leg): when enabled, an event is recorded
 // on the caller's stream before/after every kernel of trc_enc_batch_dev / trc_dec_batch_dev; trc_profile_read
 // synchronises on them and returns the milliseconds of the most recent call.  Off by default (zero overhead).
-static int g_prof = 0, g_prof_n = 0;
-static cudaEvent_t g_pev[8];
-static bool g_pev_init = false;
+// (state is per host thread: the events belong to the device that was current when the thread first profiled)
+static std::atomic<int> g_prof{0};
+static thread_local int g_prof_n = 0;
+static thread_local cudaEvent_t g_pev[8];
+static thread_local bool g_pev_init = false;
 static void prof_mark(cudaStream_t st) {
-    if (!g_prof) return;
+    if (!g_prof.load(std::memory_order_relaxed)) return;
     if (!g_pev_init) { for (auto &e : g_pev) cudaEventCreate(&e); g_pev_init = true; }
     if (g_prof_n < 8) cudaEventRecord(g_pev[g_prof_n++], st);
 }
@@ -153,6 +157,11 @@ static int dev_attrs() {
     CK(cudaFuncSetAttribute(k_rcs2_enc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem_bytes(E3_MAX_NT, true)));
     CK(cudaFuncSetAttribute(k_rcs2_enc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem_bytes(E3_MAX_NT, false)));
     CK(cudaFuncSetAttribute(k_rcs2_dec3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D3_SMEM));
+    CK(cudaFuncSetAttribute(k_rcs2_dec_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RING_W * LPC_MAX_NT * sizeof(uint32_t))));
+    CK(cudaFuncSetAttribute(k_rans_static_dec_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RING_W * LPC_MAX_NT * sizeof(uint32_t))));
+    CK(cudaFuncSetAttribute(k_ans_model3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m3_warp_bytes<true>()));
+    CK(cudaFuncSetAttribute(k_ans_code3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3_LUT_BYTES));
+    CK(cudaFuncSetAttribute(k_ans_dec3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d3_smem_bytes<true>()));
     done[d] = true;
     return TRC_OK;
 }
@@ -172,14 +181,13 @@ static int pool_keep() {
 // adaptive byte rANS encoder, third generation: model pass (one warp per unit) then coding pass (one lane per state)
 static int launch_ans_enc3(bool o1, const unsigned char *d_in, const Geom &g, uint8_t *slots, size_t slot_stride, uint32_t *recs,
                            size_t rec_stride, UnitMeta *meta, cudaStream_t st) {
-    static int s_lut_dev = -1;
-    int dev = 0; CK(cudaGetDevice(&dev));
-    if (dev != s_lut_dev) {                                     // once per process and device: attributes + reciprocal table
-        CK(cudaFuncSetAttribute(k_ans_model3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m3_warp_bytes<true>()));
-        CK(cudaFuncSetAttribute(k_ans_code3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3_LUT_BYTES));
+    static bool s_rcp[MAX_DEV];
+    int rc0 = dev_attrs(); if (rc0) return rc0;
+    const int dev = cur_dev();
+    if (!s_rcp[dev]) {                                          // once per process and device: the reciprocal table
         k_build_rcp<<<PROB_TOTAL / 256, 256, 0, st>>>();
         CK_LAUNCH();
-        s_lut_dev = dev;
+        s_rcp[dev] = true;
     }
     if (o1) k_ans_model3<true><<<(unsigned)(g.n_units < (size_t)sm_count() ? g.n_units : (size_t)sm_count()), 32, m3_warp_bytes<true>(), st>>>(d_in, g, recs, rec_stride);
     else    k_ans_model3<false><<<(unsigned)((g.n_units + M3_WPB - 1) / M3_WPB), M3_WPB * 32, M3_WPB * m3_warp_bytes<false>(), st>>>(d_in, g, recs, rec_stride);
@@ -239,8 +247,8 @@ void trc_tables_destroy(trc_tables *t) {
 const char *trc_version(void) { return "trc_b200 0.2 (sm_100a)"; }
 const char *trc_last_error(void) { return g_err; }
 int trc_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
-int trc_set_device(int dev) { g_dev = dev; CK(cudaSetDevice(dev)); return TRC_OK; }
-unsigned long long trc_launch_count(void) { return g_launches; }
+int trc_set_device(int dev) { if (dev < 0 || dev >= MAX_DEV) return TRC_E_ARG; CK(cudaSetDevice(dev)); g_dev = dev; return TRC_OK; }
+unsigned long long trc_launch_count(void) { return g_launches.load(); }
 void trc_profile_enable(int on) { g_prof = on; g_prof_n = 0; }
 int trc_profile_read(float *ms, int cap) {       // -> number of kernel intervals written (kernels of the last call)
     int n = g_prof_n - 1, k = 0;
@@ -389,15 +397,9 @@ static int enc_batch_impl(int codec, const unsigned char *d_in, size_t total_len
     case ANS4:  k_rans_adapt_enc<M_NIB, AD_NT_NIB><<<blocks(g.n_units, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta); break;
     // adaptive byte rANS: many small units -> one lane per unit (throughput); few large units -> one warp per unit (latency)
     case ANS:   if (g.n_units >= COOP_MIN_LANE_UNITS) k_rans_adapt_enc<M_BYTE, AD_NT_BYTE><<<blocks(g.n_units, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, nullptr, meta);
-                else if (g_adapt_v3) { rc = launch_ans_enc3(false, d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta, st); if (rc) return rc; }
-                else k_ans_byte_enc_coop<false><<<blocks(g.n_units, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta); break;
-    case ANS1: {
-        if (g_adapt_v3) { rc = launch_ans_enc3(true, d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta, st); if (rc) return rc; break; }
-        static bool attr = false;
-        if (!attr) { CK(cudaFuncSetAttribute(k_ans_byte_enc_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)O1_SMEM_BYTES)); attr = true; }
-        k_ans_byte_enc_coop<true><<<(unsigned)(g.n_units < 148 ? g.n_units : 148), 32, O1_SMEM_BYTES, st>>>(d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta);
-        break;
-    }
+                else { rc = launch_ans_enc3(false, d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta, st); if (rc) return rc; }
+                break;
+    case ANS1:  rc = launch_ans_enc3(true, d_in, g, slots, p.slot_stride, recs, p.rec_stride, meta, st); if (rc) return rc; break;
     case RC:    if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_enc<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, meta);
                 else k_rc_byte_enc_coop<1><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, g, slots, p.slot_stride, meta, g_force_redo); break;
     case RCI:   if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_enc<R_BYTE2, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, g, slots, p.slot_stride, meta);
@@ -470,14 +472,12 @@ static int dec_batch_impl(int codec, const unsigned char *d_in, const uint64_t *
         prof_mark(st);
         if (codec == ANSW) k_answ_dec<<<blocks(g.n_calls, ANSW_WPB), ANSW_WPB * 32, 0, st>>>(d_in, d_in_off, d_out, g, tabs, chunks_per_cdf);
         else if (codec == ANS4S) { const unsigned v2nt = v2_shape(g.n_calls, chunks_per_cdf);
-            static bool attr = false;
-            if (!attr) { CK(cudaFuncSetAttribute(k_rans_static_dec_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RING_W * LPC_MAX_NT * sizeof(uint32_t)))); attr = true; }
+            rc = dev_attrs(); if (rc) return rc;
             k_rans_static_dec_v2<<<blocks(g.n_calls, v2nt), v2nt, RING_W * v2nt * sizeof(uint32_t), st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, chunks_per_cdf, flags); }
         else if (codec == RCS) { const unsigned v2nt = v2_shape(g.n_calls, chunks_per_cdf); k_rc_static_dec_v2<1><<<blocks(g.n_calls, v2nt), v2nt, 0, st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf); }
         else { unsigned cpcta, ctas; lpc_shape(g.n_calls, chunks_per_cdf, cpcta, ctas);
                const unsigned nt = (2 * cpcta + 31) & ~31u;
-               static bool attr = false;
-               if (!attr) { CK(cudaFuncSetAttribute(k_rcs2_dec_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RING_W * LPC_MAX_NT * sizeof(uint32_t)))); attr = true; }
+               rc = dev_attrs(); if (rc) return rc;
                k_rcs2_dec_lpc<<<ctas, nt, RING_W * nt * sizeof(uint32_t), st>>>(d_in, d_in_off, d_out, g, g.n_calls, tabs, cdfnum, chunks_per_cdf, cpcta); }
         g_launches++; prof_mark(st);
         cudaError_t e = cudaPeekAtLastError();
@@ -493,22 +493,17 @@ static int dec_batch_impl(int codec, const unsigned char *d_in, const uint64_t *
     case RCS2:  k_rc_static_dec<2><<<blocks(g.n_calls, RC_SD_NT), RC_SD_NT, 0, st>>>(d_in, d_in_off, d_out, g, d_cdf, cdfnum, chunks_per_cdf); break;
     case ANS4:  k_rans_adapt_dec<M_NIB, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g, nullptr, flags); break;
     case ANS:   if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rans_adapt_dec<M_BYTE, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g, nullptr, flags);
-                else if (g_adapt_v3) k_ans_dec3<false><<<blocks(g.n_calls, 2 * D3_WPB), D3_WPB * 32, d3_smem_bytes<false>(), st>>>(d_in, d_in_off, d_out, g);
-                else k_ans_byte_dec_coop<false><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, d_in_off, d_out, g); break;
-    case ANS1: {
-        static bool attr = false;
-        if (!attr) { CK(cudaFuncSetAttribute(k_ans_byte_dec_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)O1_SMEM_BYTES));
-                     CK(cudaFuncSetAttribute(k_ans_dec3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d3_smem_bytes<true>())); attr = true; }
-        if (g_adapt_v3) k_ans_dec3<true><<<(unsigned)(g.n_calls < (size_t)sm_count() ? g.n_calls : (size_t)sm_count()), 32, d3_smem_bytes<true>(), st>>>(d_in, d_in_off, d_out, g);
-        else k_ans_byte_dec_coop<true><<<(unsigned)(g.n_calls < 148 ? g.n_calls : 148), 32, O1_SMEM_BYTES, st>>>(d_in, d_in_off, d_out, g);
-        break;
-    }
+                else k_ans_dec3<false><<<blocks(g.n_calls, 2 * D3_WPB), D3_WPB * 32, d3_smem_bytes<false>(), st>>>(d_in, d_in_off, d_out, g);
+                break;
+    case ANS1:  rc = dev_attrs(); if (rc) return rc;
+                k_ans_dec3<true><<<(unsigned)(g.n_calls < (size_t)sm_count() ? g.n_calls : (size_t)sm_count()), 32, d3_smem_bytes<true>(), st>>>(d_in, d_in_off, d_out, g);
+                break;
     case RC:    if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_dec<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g);
-                else if (g_adapt_v3) k_rc_dec3<1><<<blocks(g.n_calls, 2 * D3_WPB), D3_WPB * 32, r3_smem_bytes<1>(), st>>>(d_in, d_in_off, d_out, g);
-                else k_rc_byte_dec_coop<1><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, d_in_off, d_out, g); break;
+                else k_rc_dec3<1><<<blocks(g.n_calls, 2 * D3_WPB), D3_WPB * 32, r3_smem_bytes<1>(), st>>>(d_in, d_in_off, d_out, g);
+                break;
     case RCI:   if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_dec<R_BYTE2, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g);
-                else if (g_adapt_v3) k_rc_dec3<2><<<blocks(g.n_calls, 2 * D3_WPB), D3_WPB * 32, r3_smem_bytes<2>(), st>>>(d_in, d_in_off, d_out, g);
-                else k_rc_byte_dec_coop<2><<<blocks(g.n_calls, COOP_WPB), COOP_WPB * 32, COOP_WPB * O1_CTX_ENTRIES * 2, st>>>(d_in, d_in_off, d_out, g); break;
+                else k_rc_dec3<2><<<blocks(g.n_calls, 2 * D3_WPB), D3_WPB * 32, r3_smem_bytes<2>(), st>>>(d_in, d_in_off, d_out, g);
+                break;
     case RC4:   k_rc_adapt_dec<R_NIB1, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
     case RC4I:  k_rc_adapt_dec<R_NIB2, AD_NT_NIB><<<blocks(g.n_calls, AD_NT_NIB), AD_NT_NIB, 0, st>>>(d_in, d_in_off, d_out, g); break;
     case RC8:   k_rc_v8_dec<1><<<blocks(g.n_calls, V8_NT), V8_NT, 0, st>>>(d_in, d_in_off, d_out, g); break;
@@ -567,11 +562,29 @@ int trc_ipc_close(void *p) { CK(cudaIpcCloseMemHandle(p)); return TRC_OK; }
 int trc_memcpy_dev(void *dst, const void *src, size_t bytes, void *cuda_stream) {
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)cuda_stream)); return TRC_OK;
 }
-// copy *d_len bytes (or fixed_len when d_len is NULL; rounded up to 16) from src to dst, publish the length at dst_len
-int trc_push_dev(void *dst, const void *src, const uint64_t *d_len, size_t fixed_len, uint64_t *dst_len, void *cuda_stream) {
-    if (!dst || !src || (((uintptr_t)dst | (uintptr_t)src) & 15)) return TRC_E_ARG;
+// copy *d_len bytes (or fixed_len when d_len is NULL; rounded up to 16, at most cap when cap != 0) from src to dst, then publish
+// the length at dst_len and `seq` at dst_flag (see k_push for the completion protocol).  d_counter: one zeroed uint32 in LOCAL
+// device memory per concurrent push (NULL only with dst_flag == NULL: length published without a completion guarantee).
+// ack / ack_need (optional): do not touch dst before *ack >= ack_need (the consumer's acknowledgement of the push that used the slot last).
+int trc_push_dev(void *dst, const void *src, const uint64_t *d_len, size_t fixed_len, size_t cap, uint64_t *dst_len,
+                 uint64_t *dst_flag, uint64_t seq, unsigned int *d_counter, const uint64_t *ack, uint64_t ack_need, void *cuda_stream) {
+    if (!dst || !src || (((uintptr_t)dst | (uintptr_t)src) & 15) || (dst_flag && !d_counter)) return TRC_E_ARG;
     static const int ctas = getenv("TRC_PUSH_CTAS") ? atoi(getenv("TRC_PUSH_CTAS")) : 32;   // few CTAs: enough stores in flight for NVLink, little SM time stolen from the coders
-    k_push<<<ctas, 256, 0, (cudaStream_t)cuda_stream>>>((uint4 *)dst, (const uint4 *)src, d_len, fixed_len, dst_len);
+    k_push<<<ctas, 256, 0, (cudaStream_t)cuda_stream>>>((uint4 *)dst, (const uint4 *)src, d_len, fixed_len, cap, dst_len, dst_flag, seq, d_counter, ack, ack_need);
+    CK_LAUNCH();
+    return TRC_OK;
+}
+// block `cuda_stream` until flags[0..n) >= seq (consumer side); d_status (optional, zeroed): bit 0 set if a length overflowed its slot
+int trc_wait_flags_dev(const uint64_t *flags, const uint64_t *lens, unsigned n, uint64_t seq, unsigned int *d_status, void *cuda_stream) {
+    if (!flags || !n || n > 1024) return TRC_E_ARG;
+    k_wait_flags<<<1, (n + 31) & ~31u, 0, (cudaStream_t)cuda_stream>>>(flags, lens, n, seq, d_status);
+    CK_LAUNCH();
+    return TRC_OK;
+}
+// consumer acknowledgement: the slot set of push `seq` may be reused (stream-ordered after whatever consumed it)
+int trc_ack_dev(uint64_t *ack, uint64_t seq, void *cuda_stream) {
+    if (!ack) return TRC_E_ARG;
+    k_ack<<<1, 32, 0, (cudaStream_t)cuda_stream>>>(ack, seq);
     CK_LAUNCH();
     return TRC_OK;
 }
@@ -603,9 +616,11 @@ struct Ctx {
     DevBuf in, out, off, cdf, scratch, status;
     cudaEvent_t ev[2][64];                                           // [uploaded | coded] per sub-batch
     uint64_t *h_off = nullptr, *h_off_dev = nullptr; size_t h_off_cap = 0;   // mapped pinned staging for sub-batch offsets
+    int dev = 0;
+    // every host-pointer / drop-in entry point starts here: the calling thread is switched to the context's device
     int ensure() {
+        CK(cudaSetDevice(dev));
         if (init) return TRC_OK;
-        CK(cudaSetDevice(g_dev));
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
@@ -622,7 +637,14 @@ struct Ctx {
         h_off_cap = n + 1024; return TRC_OK;
     }
 };
-Ctx g_ctx;
+Ctx g_ctxs[MAX_DEV];                                                  // one lazily created context per device
+std::mutex g_ctxs_mu;
+Ctx &ctx_for(int dev) {
+    if (dev < 0 || dev >= MAX_DEV) dev = 0;
+    std::lock_guard<std::mutex> lk(g_ctxs_mu);
+    g_ctxs[dev].dev = dev;
+    return g_ctxs[dev];
+}
 
 // Sub-batching for the host-pointer calls: upload of sub-batch i+1, coding of i and download of i-1 overlap on
 // three streams, so a host->host call costs about max(H2D, D2H) instead of their sum.  Sub-batches are whole
@@ -724,10 +746,10 @@ static int host_dec_pipelined(Ctx &c, int codec, const unsigned char *in, const 
     return TRC_OK;
 }
 
-int host_enc(int codec, const unsigned char *in, size_t total_len, size_t chunk_len, const cdf_t *cdf, unsigned cdfnum,
+int host_enc(int dev, int codec, const unsigned char *in, size_t total_len, size_t chunk_len, const cdf_t *cdf, unsigned cdfnum,
              size_t chunks_per_cdf, unsigned char *out, uint64_t *out_off, size_t *out_len) {
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    Ctx &c = g_ctx;
+    Ctx &c = ctx_for(dev);
+    std::lock_guard<std::mutex> lk(c.mu);
     int rc = c.ensure(); if (rc) return rc;
     Plan p; rc = make_plan(codec, total_len, chunk_len, p); if (rc) return rc;
     const size_t n = p.g.n_calls;
@@ -765,10 +787,10 @@ int host_enc(int codec, const unsigned char *in, size_t total_len, size_t chunk_
 }
 
 // in_bytes: how many bytes of `in` to ship (== in_off[n] for the batch API)
-int host_dec(int codec, const unsigned char *in, const uint64_t *in_off, size_t in_bytes, unsigned char *out, size_t total_len,
+int host_dec(int dev, int codec, const unsigned char *in, const uint64_t *in_off, size_t in_bytes, unsigned char *out, size_t total_len,
              size_t chunk_len, const cdf_t *cdf, unsigned cdfnum, size_t chunks_per_cdf, unsigned flags) {
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    Ctx &c = g_ctx;
+    Ctx &c = ctx_for(dev);
+    std::lock_guard<std::mutex> lk(c.mu);
     int rc = c.ensure(); if (rc) return rc;
     Plan p; rc = make_plan(codec, total_len, chunk_len, p); if (rc) return rc;
     const size_t n = p.g.n_calls;
@@ -794,6 +816,146 @@ int host_dec(int codec, const unsigned char *in, const uint64_t *in_off, size_t 
     return TRC_OK;
 }
 
+
+// ---- one process, several GPUs (include/trc_b200.h trc_*_batch_host_multi) -----------------------------------------------
+// Chunks are independent, so the batch is cut into contiguous shards of whole chunks (whole table groups), one per device,
+// block b -> device b * n_dev / n_blocks like SURVEY.md section 8e.  One host thread per device drives its own context.
+// Encode: every device codes its shard, the threads meet once to turn the shard sizes into base offsets (the only exchange),
+// then each device downloads its packed stream straight to its place in `out`.  Decode is the mirror: the chunk directory
+// (in_off) tells every device which slice of the stream it needs; nothing is exchanged.
+struct Shard { size_t c0, c1; };                                      // chunk range
+static void make_shards(size_t n_chunks, size_t cpc, int n_dev, std::vector<Shard> &sh) {
+    const size_t grp = cpc ? cpc : 1, n_grp = (n_chunks + grp - 1) / grp;
+    sh.resize(n_dev);
+    for (int r = 0; r < n_dev; r++) {
+        size_t a = ((size_t)r * n_grp + n_dev - 1) / n_dev * grp, b = ((size_t)(r + 1) * n_grp + n_dev - 1) / n_dev * grp;
+        sh[r].c0 = a < n_chunks ? a : n_chunks; sh[r].c1 = b < n_chunks ? b : n_chunks;
+    }
+}
+struct SpinBarrier {                                                  // the threads of one call meet once or twice: no need for anything heavier
+    std::atomic<int> count{0}, phase{0}; int n;
+    explicit SpinBarrier(int n_) : n(n_) {}
+    void wait() {
+        const int ph = phase.load();
+        if (count.fetch_add(1) + 1 == n) { count.store(0); phase.store(ph + 1); }
+        else while (phase.load() == ph) std::this_thread::yield();
+    }
+};
+
+static int multi_enc(int codec, const int *devs, int n_dev, const unsigned char *in, size_t total_len, size_t chunk_len, const cdf_t *cdf,
+                     unsigned cdfnum, size_t cpc, unsigned char *out, uint64_t *out_off, size_t *out_len) {
+    const size_t n = trc_num_chunks(total_len, chunk_len);
+    std::vector<Shard> sh; make_shards(n, cpc, n_dev, sh);
+    std::vector<uint64_t> size(n_dev, 0), base(n_dev + 1, 0);
+    std::vector<int> rcs(n_dev, TRC_OK);
+    std::vector<std::string> errs(n_dev);
+    std::vector<std::vector<uint64_t>> offs(n_dev);
+    SpinBarrier bar(n_dev);
+    auto work = [&](int r) {
+        const Shard s = sh[r];
+        const size_t nc = s.c1 - s.c0, b0 = s.c0 * chunk_len, len = nc ? (s.c1 * chunk_len < total_len ? s.c1 * chunk_len : total_len) - b0 : 0;
+        Ctx &c = ctx_for(devs[r]);
+        std::unique_lock<std::mutex> lk(c.mu);
+        int rc = TRC_OK;
+        Plan p;
+        auto phase_a = [&]() -> int {
+            if (!nc) return TRC_OK;
+            int q;
+            if ((q = c.ensure()) || (q = make_plan(codec, len, chunk_len, p))) return q;
+            if ((q = c.in.need(len + 64)) || (q = c.out.need(trc_enc_bound(len, chunk_len))) || (q = c.off.need((nc + 1) * 8)) || (q = c.scratch.need(p.total + 256))) return q;
+            CK(cudaMemcpyAsync(c.in.p, in + b0, len, cudaMemcpyHostToDevice, c.st));
+            if (codec_static(codec)) {
+                if (!cdf) return TRC_E_ARG;
+                const size_t nt = n_tables(nc, cpc), t0 = cpc ? s.c0 / cpc : 0, bytes = ((nt - 1) * CDF_STRIDE + cdfnum + 1) * sizeof(cdf_t);
+                if ((q = c.cdf.need(nt * CDF_STRIDE * sizeof(cdf_t)))) return q;
+                CK(cudaMemcpyAsync(c.cdf.p, cdf + t0 * CDF_STRIDE, bytes, cudaMemcpyHostToDevice, c.st));
+            }
+            q = trc_enc_batch_dev(codec, (const unsigned char *)c.in.p, len, chunk_len, (const cdf_t *)c.cdf.p, cdfnum, cpc, (unsigned char *)c.out.p,
+                                  (uint64_t *)c.off.p, c.scratch.p, c.scratch.cap, c.st);
+            if (q) return q;
+            offs[r].resize(nc + 1);
+            CK(cudaMemcpyAsync(offs[r].data(), c.off.p, (nc + 1) * 8, cudaMemcpyDeviceToHost, c.st));
+            CK(cudaStreamSynchronize(c.st));
+            size[r] = offs[r][nc];
+            return TRC_OK;
+        };
+        rc = phase_a();
+        if (rc) { rcs[r] = rc; errs[r] = g_err; }
+        bar.wait();                                                   // the one exchange: shard sizes -> base offsets
+        uint64_t b = 0;
+        for (int k = 0; k < r; k++) b += size[k];
+        bool any_err = false;
+        for (int k = 0; k < n_dev; k++) any_err |= rcs[k] != TRC_OK;
+        if (!any_err && nc) {
+            auto phase_b = [&]() -> int {
+                CK(cudaMemcpyAsync(out + b, c.out.p, (size_t)size[r], cudaMemcpyDeviceToHost, c.st));
+                if (out_off) for (size_t k = 0; k < nc; k++) out_off[s.c0 + k] = b + offs[r][k];
+                CK(cudaStreamSynchronize(c.st));
+                return TRC_OK;
+            };
+            rc = phase_b();
+            if (rc) { rcs[r] = rc; errs[r] = g_err; }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < n_dev; r++) th.emplace_back(work, r);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int r = 0; r < n_dev; r++) if (rcs[r]) { snprintf(g_err, sizeof g_err, "device %d: %s", devs[r], errs[r].c_str()); return rcs[r]; }
+    uint64_t tot = 0;
+    for (int r = 0; r < n_dev; r++) tot += size[r];
+    if (out_off) out_off[n] = tot;
+    if (out_len) *out_len = (size_t)tot;
+    return TRC_OK;
+}
+
+static int multi_dec(int codec, const int *devs, int n_dev, const unsigned char *in, const uint64_t *in_off, unsigned char *out, size_t total_len,
+                     size_t chunk_len, const cdf_t *cdf, unsigned cdfnum, size_t cpc, unsigned flags) {
+    const size_t n = trc_num_chunks(total_len, chunk_len);
+    std::vector<Shard> sh; make_shards(n, cpc, n_dev, sh);
+    std::vector<int> rcs(n_dev, TRC_OK);
+    std::vector<std::string> errs(n_dev);
+    auto work = [&](int r) {
+        const Shard s = sh[r];
+        const size_t nc = s.c1 - s.c0;
+        if (!nc) return;
+        const size_t b0 = s.c0 * chunk_len, len = (s.c1 * chunk_len < total_len ? s.c1 * chunk_len : total_len) - b0;
+        const uint64_t s0 = in_off[s.c0], s1 = in_off[s.c1];
+        Ctx &c = ctx_for(devs[r]);
+        std::lock_guard<std::mutex> lk(c.mu);
+        std::vector<uint64_t> roff(nc + 1);                           // this shard's directory, relative to its first byte
+        for (size_t k = 0; k <= nc; k++) roff[k] = in_off[s.c0 + k] - s0;
+        auto run = [&]() -> int {
+            int q;
+            if ((q = c.ensure())) return q;
+            if ((q = c.in.need((size_t)(s1 - s0) + 64)) || (q = c.out.need(len + 64)) || (q = c.off.need((nc + 1) * 8))) return q;
+            CK(cudaMemcpyAsync(c.off.p, roff.data(), (nc + 1) * 8, cudaMemcpyHostToDevice, c.st));
+            CK(cudaMemcpyAsync(c.in.p, in + s0, (size_t)(s1 - s0), cudaMemcpyHostToDevice, c.st));
+            CK(cudaMemsetAsync((uint8_t *)c.in.p + (s1 - s0), 0, 64, c.st));
+            if (codec_static(codec)) {
+                if (!cdf) return TRC_E_ARG;
+                const size_t nt = n_tables(nc, cpc), t0 = cpc ? s.c0 / cpc : 0, bytes = ((nt - 1) * CDF_STRIDE + cdfnum + 1) * sizeof(cdf_t);
+                if ((q = c.cdf.need(nt * CDF_STRIDE * sizeof(cdf_t)))) return q;
+                CK(cudaMemcpyAsync(c.cdf.p, cdf + t0 * CDF_STRIDE, bytes, cudaMemcpyHostToDevice, c.st));
+            }
+            q = trc_dec_batch_dev(codec, (const unsigned char *)c.in.p, (const uint64_t *)c.off.p, (unsigned char *)c.out.p, len, chunk_len,
+                                  (const cdf_t *)c.cdf.p, cdfnum, cpc, flags, c.st);
+            if (q) return q;
+            CK(cudaMemcpyAsync(out + b0, c.out.p, len, cudaMemcpyDeviceToHost, c.st));
+            CK(cudaStreamSynchronize(c.st));
+            return TRC_OK;
+        };
+        const int rc = run();
+        if (rc) { rcs[r] = rc; errs[r] = g_err; }
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < n_dev; r++) th.emplace_back(work, r);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int r = 0; r < n_dev; r++) if (rcs[r]) { snprintf(g_err, sizeof g_err, "device %d: %s", devs[r], errs[r].c_str()); return rcs[r]; }
+    return TRC_OK;
+}
+
 [[noreturn]] void die_cuda(const char *fn, int rc) {          // mirrors die() include_/conf.h:379
     fprintf(stderr, "trc_b200: %s failed (%d): %s\n", fn, rc, g_err);
     fflush(stderr);
@@ -809,7 +971,7 @@ size_t dropin_enc(const char *fn, int codec, unsigned char *in, size_t inlen, un
         return 0;
     }
     size_t l = 0;
-    int rc = host_enc(codec, in, inlen, inlen, cdf, cdfnum, 0, out, nullptr, &l);
+    int rc = host_enc(g_dev, codec, in, inlen, inlen, cdf, cdfnum, 0, out, nullptr, &l);
     if (rc) die_cuda(fn, rc);
     return l;
 }
@@ -820,12 +982,13 @@ size_t dropin_dec(const char *fn, int codec, unsigned char *in, size_t outlen, u
     if (outlen == 0) return 0;
     uint64_t off[2] = { 0, (uint64_t)outlen + 8 };             // != outlen, so the call is never taken for raw
     {
-        std::lock_guard<std::mutex> lk(g_ctx.mu);
-        int rc = g_ctx.ensure(); if (rc) die_cuda(fn, rc);
-        if ((rc = g_ctx.in.need(outlen + 64))) die_cuda(fn, rc);
-        if (cudaMemsetAsync((uint8_t *)g_ctx.in.p + outlen, 0, 64, g_ctx.st) != cudaSuccess) die_cuda(fn, TRC_E_CUDA);
+        Ctx &c = ctx_for(g_dev);
+        std::lock_guard<std::mutex> lk(c.mu);
+        int rc = c.ensure(); if (rc) die_cuda(fn, rc);
+        if ((rc = c.in.need(outlen + 64))) die_cuda(fn, rc);
+        if (cudaMemsetAsync((uint8_t *)c.in.p + outlen, 0, 64, c.st) != cudaSuccess) die_cuda(fn, TRC_E_CUDA);
     }
-    int rc = host_dec(codec, in, off, outlen, out, outlen, outlen, cdf, cdfnum, 0, flags);
+    int rc = host_dec(g_dev, codec, in, off, outlen, out, outlen, outlen, cdf, cdfnum, 0, flags);
     if (rc) die_cuda(fn, rc);
     return outlen;
 }
@@ -833,18 +996,42 @@ size_t dropin_dec(const char *fn, int codec, unsigned char *in, size_t outlen, u
 
 extern "C" {
 
+static int check_devs(const int *devs, int n_dev) {
+    if (!devs || n_dev < 1 || n_dev > MAX_DEV) return TRC_E_ARG;
+    const int have = trc_device_count();
+    for (int r = 0; r < n_dev; r++) {
+        if (devs[r] < 0 || devs[r] >= have || devs[r] >= MAX_DEV) return TRC_E_ARG;
+        for (int k = 0; k < r; k++) if (devs[k] == devs[r]) return TRC_E_ARG;
+    }
+    return TRC_OK;
+}
+int trc_enc_batch_host_multi(int codec, const int *devs, int n_dev, const unsigned char *in, size_t total_len, size_t chunk_len,
+                             const cdf_t *cdf, unsigned cdfnum, size_t chunks_per_cdf,
+                             unsigned char *out, uint64_t *out_off, size_t *out_len) {
+    if (!in || !out || !chunk_len || !total_len || codec < 0 || codec >= NCODECS) return TRC_E_ARG;
+    int rc = check_devs(devs, n_dev); if (rc) return rc;
+    return multi_enc(codec, devs, n_dev, in, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, out, out_off, out_len);
+}
+int trc_dec_batch_host_multi(int codec, const int *devs, int n_dev, const unsigned char *in, const uint64_t *in_off,
+                             unsigned char *out, size_t total_len, size_t chunk_len,
+                             const cdf_t *cdf, unsigned cdfnum, size_t chunks_per_cdf, unsigned flags) {
+    if (!in || !in_off || !out || !chunk_len || !total_len || codec < 0 || codec >= NCODECS) return TRC_E_ARG;
+    int rc = check_devs(devs, n_dev); if (rc) return rc;
+    return multi_dec(codec, devs, n_dev, in, in_off, out, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, flags);
+}
+
 int trc_enc_batch_host(int codec, const unsigned char *in, size_t total_len, size_t chunk_len,
                        const cdf_t *cdf, unsigned cdfnum, size_t chunks_per_cdf,
                        unsigned char *out, uint64_t *out_off, size_t *out_len) {
     if (!in || !out) return TRC_E_ARG;
-    return host_enc(codec, in, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, out, out_off, out_len);
+    return host_enc(g_dev, codec, in, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, out, out_off, out_len);
 }
 int trc_dec_batch_host(int codec, const unsigned char *in, const uint64_t *in_off,
                        unsigned char *out, size_t total_len, size_t chunk_len,
                        const cdf_t *cdf, unsigned cdfnum, size_t chunks_per_cdf, unsigned flags) {
     if (!in || !in_off || !out || !chunk_len) return TRC_E_ARG;
     size_t n = trc_num_chunks(total_len, chunk_len);
-    return host_dec(codec, in, in_off, (size_t)in_off[n], out, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, flags);
+    return host_dec(g_dev, codec, in, in_off, (size_t)in_off[n], out, total_len, chunk_len, cdf, cdfnum, chunks_per_cdf, flags);
 }
 
 // ---- self-describing container ---------------------------------------------------------
@@ -908,8 +1095,8 @@ int trc_compress_host(int codec, const unsigned char *in, size_t total_len, size
     if (!in || !out) return TRC_E_ARG;
     CtLayout L; int rc = ct_layout(codec, total_len, chunk_len, cdf_block, L); if (rc) return rc;
     if (out_cap < L.off_payload + trc_enc_bound(total_len, chunk_len)) return TRC_E_NOMEM;
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    Ctx &c = g_ctx;
+    Ctx &c = ctx_for(g_dev);
+    std::lock_guard<std::mutex> lk(c.mu);
     if ((rc = c.ensure())) return rc;
     Plan p; if ((rc = make_plan(codec, total_len, chunk_len, p))) return rc;
     if ((rc = c.in.need(total_len + 64)) || (rc = c.out.need(trc_enc_bound(total_len, chunk_len))) || (rc = c.off.need((L.n + 1) * 8)) ||
@@ -962,8 +1149,8 @@ int trc_decompress_host(const unsigned char *in, size_t in_len, unsigned char *o
         off[k + 1] = off[k] + cl;
     }
     if (off[n] != h.payload_bytes) return TRC_E_ARG;
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    Ctx &c = g_ctx;
+    Ctx &c = ctx_for(g_dev);
+    std::lock_guard<std::mutex> lk(c.mu);
     if ((rc = c.ensure())) return rc;
     if ((rc = c.in.need((size_t)h.payload_bytes + 64)) || (rc = c.out.need(total_len + 64)) || (rc = c.off.need((n + 1) * 8)) ||
         (rc = c.cdf.need((L.ntab + 1) * CDF_STRIDE * sizeof(cdf_t)))) return rc;
@@ -981,7 +1168,7 @@ int trc_decompress_host(const unsigned char *in, size_t in_len, unsigned char *o
 }
 
 // ---- drop-in layer ----------------------------------------------------------------------------------------
-void anscdfini(unsigned id) { (void)id; std::lock_guard<std::mutex> lk(g_ctx.mu); int rc = g_ctx.ensure(); if (rc) die_cuda("anscdfini", rc); }
+void anscdfini(unsigned id) { (void)id; Ctx &c = ctx_for(g_dev); std::lock_guard<std::mutex> lk(c.mu); int rc = c.ensure(); if (rc) die_cuda("anscdfini", rc); }
 
 #define ENC3(name, codec) size_t name(unsigned char *in, size_t inlen, unsigned char *out) { return dropin_enc(#name, codec, in, inlen, out, nullptr, 0); }
 #define DEC3(name, codec, fl) size_t name(unsigned char *in, size_t outlen, unsigned char *out) { return dropin_dec(#name, codec, in, outlen, out, nullptr, 0, fl); }
@@ -1020,8 +1207,8 @@ int cdfini(unsigned char *in, size_t inlen, cdf_t *cdf, unsigned cdfnum) {
     if (inlen == 0 || cdfnum == 0 || cdfnum > 256) { fprintf(stderr, "Fatal cdf: empty input\n"); exit(-1); }
     int status = 0;
     {
-        std::lock_guard<std::mutex> lk(g_ctx.mu);
-        Ctx &c = g_ctx;
+        Ctx &c = ctx_for(g_dev);
+        std::lock_guard<std::mutex> lk(c.mu);
         int rc = c.ensure(); if (rc) die_cuda("cdfini", rc);
         if ((rc = c.in.need(inlen + 64)) || (rc = c.cdf.need(CDF_STRIDE * sizeof(cdf_t))) || (rc = c.status.need(64))) die_cuda("cdfini", rc);
         if (cudaMemcpyAsync(c.in.p, in, inlen, cudaMemcpyHostToDevice, c.st) != cudaSuccess) die_cuda("cdfini", TRC_E_CUDA);

@@ -55,28 +55,39 @@ def gather_compressed(payload: torch.Tensor, dst: int = 0, group=None, out: torc
 class PeerGather:
     """Gather of the packed streams over NVLink peer memory, driven from the device (CUDA only).
 
-    Rank `dst` owns a buffer of world x slot_bytes (+ one length word per rank); every rank maps it through CUDA IPC
-    and `push()` launches a copy kernel that reads the byte count from device memory (the encoder's out_off[n]) and
-    stores the stream into slot `rank` -- for remote ranks the 128-bit stores cross NVSwitch.  Nothing synchronises
-    with the host and no collective is called per step, so the transfer overlaps whatever runs on other streams.
-    Layout on `dst`: slot r at r*slot_bytes, lengths (uint64) at world*slot_bytes + 8*r.
+    Rank `dst` owns `depth` sets of world x slot_bytes slots (+ one length and one flag word per slot); every rank maps the
+    buffer through CUDA IPC.  `push()` launches a copy kernel that reads the byte count from device memory (the encoder's
+    out_off[n]) and stores the stream into slot (seq % depth, rank) -- for remote ranks the 128-bit stores cross NVSwitch --
+    then publishes length and sequence number with release semantics (csrc/pack.cuh k_push).  `wait_all(seq)` on `dst` blocks
+    a stream until every rank's push `seq` has landed: after it the gathered streams can be consumed on the device.
+    `fetch()` is the mirror (scatter by the directory): a rank copies a slot of the gathered buffer back into local memory.
+    Nothing synchronises with the host and no collective is called per step.
+    Layout on `dst`: slot (d, r) at (d*world + r)*slot_bytes; lengths then flags (uint64 each) behind the slots.
     """
 
-    def __init__(self, slot_bytes: int, dst: int = 0, group=None):
+    def __init__(self, slot_bytes: int, dst: int = 0, group=None, depth: int = 2):
         import ctypes
         import importlib
         self.ct = ctypes
         self.trc = importlib.import_module("turbo-range-coder_b200")
         lib = self.trc.lib
-        for f in (lib.trc_dev_alloc, lib.trc_ipc_export, lib.trc_ipc_open, lib.trc_ipc_close, lib.trc_push_dev, lib.trc_memcpy_dev, lib.trc_dev_free):
+        for f in (lib.trc_dev_alloc, lib.trc_ipc_export, lib.trc_ipc_open, lib.trc_ipc_close, lib.trc_push_dev, lib.trc_wait_flags_dev, lib.trc_ack_dev,
+                  lib.trc_memcpy_dev, lib.trc_dev_free):
             f.restype = ctypes.c_int
-        self.world, self.rank, self.dst, self.group = dist.get_world_size(group), dist.get_rank(group), dst, group
+        self.world, self.rank, self.dst, self.group, self.depth = dist.get_world_size(group), dist.get_rank(group), dst, group, depth
         self.slot_bytes = (int(slot_bytes) + 255) & ~255
-        total = self.world * self.slot_bytes + 8 * self.world + 256
+        nslot = depth * self.world
+        self.off_lens = nslot * self.slot_bytes
+        self.off_flags = self.off_lens + 8 * nslot
+        self.off_status = self.off_flags + 8 * nslot
+        self.off_ack = self.off_status + 64                 # one acknowledgement word per slot set
+        total = self.off_ack + 8 * depth + 256
         self.base = ctypes.c_void_p()
+        self.local = ctypes.c_void_p()                      # local scratch: completion counters of this rank's pushes (one per depth)
+        self.trc._check(lib.trc_dev_alloc(ctypes.byref(self.local), ctypes.c_size_t(256)), "trc_dev_alloc")
         handle = [None]
         if self.rank == dst:
-            self.trc._check(lib.trc_dev_alloc(ctypes.byref(self.base), ctypes.c_size_t(total)), "trc_dev_alloc")
+            self.trc._check(lib.trc_dev_alloc(ctypes.byref(self.base), ctypes.c_size_t(total)), "trc_dev_alloc")   # zeroed
             h = (ctypes.c_ubyte * 64)()
             self.trc._check(lib.trc_ipc_export(self.base, h), "trc_ipc_export")
             handle = [bytes(h)]
@@ -85,35 +96,90 @@ class PeerGather:
             h = (ctypes.c_ubyte * 64).from_buffer_copy(handle[0])
             self.trc._check(lib.trc_ipc_open(h, ctypes.byref(self.base)), "trc_ipc_open")
         self.total = total
+        self.seq = 0                                        # pushes issued by this rank so far
 
-    def slot_ptr(self, r):
-        return self.base.value + r * self.slot_bytes
+    def _slot(self, d, r):
+        return d * self.world + r
 
-    def len_ptr(self, r):
-        return self.base.value + self.world * self.slot_bytes + 8 * r
+    def slot_ptr(self, r, seq=None):
+        d = (self.seq if seq is None else seq) % self.depth
+        return self.base.value + self._slot(d, r) * self.slot_bytes
 
-    def push(self, payload: torch.Tensor, d_len_ptr: int, stream=None):
-        """payload: the local packed stream buffer (16-byte aligned); d_len_ptr: device address of its uint64 length."""
+    def len_ptr(self, r, seq=None):
+        d = (self.seq if seq is None else seq) % self.depth
+        return self.base.value + self.off_lens + 8 * self._slot(d, r)
+
+    def flag_ptr(self, r, seq=None):
+        d = (self.seq if seq is None else seq) % self.depth
+        return self.base.value + self.off_flags + 8 * self._slot(d, r)
+
+    def push(self, payload: torch.Tensor, d_len_ptr: int, stream=None) -> int:
+        """payload: the local packed stream buffer (16-byte aligned); d_len_ptr: device address of its uint64 length.
+        Returns the sequence number of this push (1, 2, ...): the same number on every rank names the same step."""
         st = stream if stream is not None else torch.cuda.current_stream()
-        rc = self.trc.lib.trc_push_dev(self.ct.c_void_p(self.slot_ptr(self.rank)), self.ct.c_void_p(payload.data_ptr()),
-                                       self.ct.c_void_p(d_len_ptr), self.ct.c_size_t(0), self.ct.c_void_p(self.len_ptr(self.rank)),
-                                       self.ct.c_void_p(st.cuda_stream))
+        self.seq += 1
+        s, ct = self.seq, self.ct
+        rc = self.trc.lib.trc_push_dev(ct.c_void_p(self.slot_ptr(self.rank, s)), ct.c_void_p(payload.data_ptr()), ct.c_void_p(d_len_ptr),
+                                       ct.c_size_t(0), ct.c_size_t(self.slot_bytes), ct.c_void_p(self.len_ptr(self.rank, s)),
+                                       ct.c_void_p(self.flag_ptr(self.rank, s)), ct.c_uint64(s),
+                                       ct.c_void_p(self.local.value + 4 * (s % self.depth)),
+                                       ct.c_void_p(self.base.value + self.off_ack + 8 * (s % self.depth)), ct.c_uint64(max(0, s - self.depth)),
+                                       ct.c_void_p(st.cuda_stream))
         self.trc._check(rc, "trc_push_dev")
+        return s
 
-    def read_slot(self, r, nbytes, device):
+    def wait_all(self, seq: int, stream=None):
+        """(dst only) make `stream` wait until push `seq` of every rank has landed (flags acquired on the device)."""
+        assert self.rank == self.dst
+        st = stream if stream is not None else torch.cuda.current_stream()
+        ct, d = self.ct, seq % self.depth
+        rc = self.trc.lib.trc_wait_flags_dev(ct.c_void_p(self.base.value + self.off_flags + 8 * self._slot(d, 0)),
+                                             ct.c_void_p(self.base.value + self.off_lens + 8 * self._slot(d, 0)), ct.c_uint(self.world),
+                                             ct.c_uint64(seq), ct.c_void_p(self.base.value + self.off_status), ct.c_void_p(st.cuda_stream))
+        self.trc._check(rc, "trc_wait_flags_dev")
+
+    def ack(self, seq: int, stream=None):
+        """(dst only) the consumer is done with the slot set of push `seq` (stream-ordered): producers may overwrite it.
+        push() of step seq + depth waits for this on the device -- without it a fast producer would lap the consumer."""
+        assert self.rank == self.dst
+        st = stream if stream is not None else torch.cuda.current_stream()
+        rc = self.trc.lib.trc_ack_dev(self.ct.c_void_p(self.base.value + self.off_ack + 8 * (seq % self.depth)), self.ct.c_uint64(seq),
+                                      self.ct.c_void_p(st.cuda_stream))
+        self.trc._check(rc, "trc_ack_dev")
+
+    def fetch(self, r: int, seq: int, out: torch.Tensor, stream=None):
+        """The mirror of push (scatter by the directory): copy slot (seq, r) of the gathered buffer -- its byte count is read from
+        the gathered lengths, on the device -- into the local tensor `out`.  The caller orders this after the slot is complete
+        (own slot: stream order after push(); any slot on dst: after wait_all())."""
+        st = stream if stream is not None else torch.cuda.current_stream()
+        ct = self.ct
+        rc = self.trc.lib.trc_push_dev(ct.c_void_p(out.data_ptr()), ct.c_void_p(self.slot_ptr(r, seq)), ct.c_void_p(self.len_ptr(r, seq)),
+                                       ct.c_size_t(0), ct.c_size_t(out.numel() & ~15), None, None, ct.c_uint64(0), None, None, ct.c_uint64(0),
+                                       ct.c_void_p(st.cuda_stream))
+        self.trc._check(rc, "trc_push_dev (fetch)")
+
+    def read_slot(self, r, nbytes, device, seq=None):
         """(dst only) copy slot r into a fresh tensor -- verification helper."""
         out = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        rc = self.trc.lib.trc_memcpy_dev(self.ct.c_void_p(out.data_ptr()), self.ct.c_void_p(self.slot_ptr(r)), self.ct.c_size_t(nbytes),
+        rc = self.trc.lib.trc_memcpy_dev(self.ct.c_void_p(out.data_ptr()), self.ct.c_void_p(self.slot_ptr(r, seq)), self.ct.c_size_t(nbytes),
                                          self.ct.c_void_p(torch.cuda.current_stream().cuda_stream))
         self.trc._check(rc, "trc_memcpy_dev")
         return out
 
-    def read_lens(self, device):
+    def read_lens(self, device, seq=None):
         out = torch.empty(self.world, dtype=torch.int64, device=device)
-        rc = self.trc.lib.trc_memcpy_dev(self.ct.c_void_p(out.data_ptr()), self.ct.c_void_p(self.len_ptr(0)), self.ct.c_size_t(8 * self.world),
+        rc = self.trc.lib.trc_memcpy_dev(self.ct.c_void_p(out.data_ptr()), self.ct.c_void_p(self.len_ptr(0, seq)), self.ct.c_size_t(8 * self.world),
                                          self.ct.c_void_p(torch.cuda.current_stream().cuda_stream))
         self.trc._check(rc, "trc_memcpy_dev")
         return out
+
+    def overflowed(self, device) -> bool:
+        """(dst only) did any pushed stream exceed its slot?  (reads the status word written by wait_all)"""
+        out = torch.empty(1, dtype=torch.int32, device=device)
+        rc = self.trc.lib.trc_memcpy_dev(self.ct.c_void_p(out.data_ptr()), self.ct.c_void_p(self.base.value + self.off_status), self.ct.c_size_t(4),
+                                         self.ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+        self.trc._check(rc, "trc_memcpy_dev")
+        return bool(int(out.item()) & 1)
 
     def close(self):
         if self.base.value:
@@ -122,3 +188,6 @@ class PeerGather:
             else:
                 self.trc.lib.trc_ipc_close(self.base)
             self.base = self.ct.c_void_p()
+        if self.local.value:
+            self.trc.lib.trc_dev_free(self.local)
+            self.local = self.ct.c_void_p()
