@@ -16,6 +16,13 @@
  *   97   drop-in symbol anscdfenc / anscdfdec    of libtrc_b200.so (whole buffer; same bytes as id 56)
  *   98   TRC_RC8   rccdfenc8  / rccdfdec8,   4 KiB chunks               48
  *   99   TRC_RCI8  rccdfienc8 / rccdfidec8,  4 KiB chunks               49
+ *   70   TRC_RCU16/32   rccdfuenc  / rccdfudec   (Turbo vlc6), 4 KiB chunks    50      (-Os2 / -Os4 select the integer width, like
+ *   72   TRC_RCV16/32   rccdfvenc  / rccdfvdec   (Turbo vlc7)                  52       the reference ids; input length must be whole
+ *   73   TRC_RCVZ16/32  rccdfvzenc / rccdfvzdec  (vlc7 zigzag)                 53       integers)
+ *   74   TRC_ANSU16     anscdfuenc16  / anscdfudec16                           60
+ *   75   TRC_ANSUZ16    anscdfuzenc16 / anscdfuzdec16                          61
+ *   76   TRC_ANSV16/32  anscdfvenc / anscdfvdec                                62
+ *   77   TRC_ANSVZ16/32 anscdfvzenc / anscdfvzdec                              63
  * Chunk sizes can be overridden with the environment variable TRC_CHUNK (bytes).
  */
 #ifndef XTURBORC_H_

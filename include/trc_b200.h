@@ -129,8 +129,10 @@ int trc_dec_batch_host(int codec, const unsigned char *in, const uint64_t *in_of
 
 /* Static tables on the device: table c = cdfini(chunk c) (reference rccdf.c:50-68 semantics), chunking as
  * above (use a large chunk_len here, e.g. the whole buffer or a 64 MB block).  d_cdf receives n tables of
- * TRC_CDF_STRIDE entries.  Returns TRC_E_ARG if any table is degenerate (the reference
- * would die()); d_status (n ints, may be NULL) gets 0/-1 per chunk. */
+ * TRC_CDF_STRIDE entries (entries past cdfnum are zero).  The call is asynchronous and returns TRC_OK once the kernels are
+ * queued: whether table c is usable is reported in d_status[c] (n ints on the device, 0 = fine, -1 = degenerate table -- the
+ * reference would die(), rccdf.c:65-66 -- or a byte >= cdfnum in the chunk, which the reference leaves to its caller,
+ * turborc.c:535).  Pass d_status and read it before trusting the tables; NULL skips the report. */
 int trc_cdfini_batch_dev(const unsigned char *d_in, size_t total_len, size_t chunk_len,
                          cdf_t *d_cdf, unsigned cdfnum, int *d_status, void *cuda_stream);
 

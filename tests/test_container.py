@@ -72,3 +72,40 @@ def test_container_rejects_corrupt_directory(trc, dg):
     blob[dir_off:dir_off + 4] = np.frombuffer(struct.pack("<I", 1 << 30), np.uint8)   # a chunk longer than its input
     with pytest.raises(trc.TrcError):
         trc.decompress(blob)
+
+
+@pytest.mark.gpu
+def test_container_ans4s_rejects_bytes_outside_the_alphabet(trc, dg):
+    """TRC_ANS4S codes a 16-symbol alphabet (anscdf.c:57; the harness guards it at the caller, turborc.c:535 `if(m<16)`): a byte
+    >= 16 must be reported, not silently coded with an empty table entry."""
+    d = dg.nibbles(dg.zipf(50_000, seed=4))
+    blob = trc.compress(trc.ANS4S, d, 4096)
+    assert np.array_equal(trc.decompress(blob), d)
+    # the table rows travel in the container: entries past the alphabet are defined (zero), so the bytes are reproducible
+    assert np.array_equal(blob, trc.compress(trc.ANS4S, d, 4096))
+    bad = d.copy(); bad[1234] = 200
+    with pytest.raises(trc.TrcError):
+        trc.compress(trc.ANS4S, bad, 4096)
+
+
+@pytest.mark.gpu
+def test_container_corrupt_payload_does_not_crash(trc, dg):
+    """A damaged payload decodes to garbage or is rejected, but never reads or writes out of bounds (ring decoders clamp)."""
+    d = dg.zipf(300_000, seed=8)
+    for codec in (trc.RCS2, trc.ANS4S, trc.RCS, trc.ANS, trc.RC):
+        x = dg.nibbles(d) if codec == trc.ANS4S else d
+        blob = trc.compress(codec, x, 1760 if codec == trc.RCS2 else 4096).copy()
+        rng = np.random.default_rng(codec)
+        hdr = trc.CONTAINER_HEADER
+        for _ in range(3):
+            b = blob.copy()
+            pos = rng.integers(blob.size // 2, blob.size, 64)
+            b[pos] ^= rng.integers(1, 256, 64).astype(np.uint8)
+            try:
+                out = trc.decompress(b)
+                assert out.size == x.size
+            except trc.TrcError:
+                pass
+        t = blob[: hdr + (blob.size - hdr) // 2]                   # truncated
+        with pytest.raises(trc.TrcError):
+            trc.decompress(t)

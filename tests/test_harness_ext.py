@@ -73,3 +73,31 @@ def test_harness_gpu_rows(tmp_path, dg, port):
         else:
             _, off = cpu_batch(port, 3, data, 4194304, None, 0)
             assert rows[94] == int(off[-1]) == rows[64]                              # one 4 MiB chunk == the whole 3 MB call
+
+
+@pytest.mark.gpu
+def test_harness_gpu_vlc_rows(tmp_path, port):
+    """GPU batch rows for the VLC-over-CDF integer ids (70-77; 80-87 are taken by the reference's transforms) next to the reference's 50-53 / 60-63: round trip checked by the
+    harness's own memcheck, compressed sizes equal to the oracle's per-chunk calls."""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/turborc_gpu not built")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from vlc_data import sources
+    from oracle import cpu
+    pairs16 = {70: "rccdfuenc16", 72: "rccdfvenc16", 73: "rccdfvzenc16", 74: "anscdfuenc16", 75: "anscdfuzenc16", 76: "anscdfvenc16", 77: "anscdfvzenc16"}
+    pairs32 = {70: "rccdfuenc32", 72: "rccdfvenc32", 73: "rccdfvzenc32", 76: "anscdfvenc32", 77: "anscdfvzenc32"}
+    for width, flag, pairs, ref_ids in ((16, "-Os", pairs16, "50,52,53,60,61,62,63"), (32, "-Ou", pairs32, "50,52,53,62,63")):
+        data = sources(width, 400_000)["walk"]
+        src = tmp_path / f"w{width}.bin"
+        data.tofile(src)
+        ids = ",".join(str(k) for k in sorted(pairs))
+        r = subprocess.run([BIN, "-I1", "-J1", flag, "-e" + ref_ids + "," + ids, str(src)], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "ERROR" not in (r.stdout + r.stderr).upper(), r.stdout + r.stderr
+        rows = _rows(r.stdout)
+        raw = data.view(np.uint8)
+        for ident, enc in pairs.items():
+            assert ident in rows, (ident, r.stdout)
+            _, off = cpu.batch_enc(cpu.port(), enc, raw, 4096)
+            assert rows[ident] == int(off[-1]), (width, ident, rows[ident], int(off[-1]))

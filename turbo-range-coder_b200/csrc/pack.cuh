@@ -294,6 +294,10 @@ __global__ void k_cdf_finalize(Geom g, const unsigned long long *__restrict__ hi
         if (prev >= (cdf_t)acc) bad = 1;                                // the reference die()s here (rccdf.c:65)
     }
     if ((cdf_t)acc != (cdf_t)PROB_TOTAL) bad = 1;                       // rccdf.c:66
+    // a symbol outside the alphabet would be coded with an all-zero table entry (the reference leaves that to its caller:
+    // turborc.c:535 `if(m<16)`): report it like a degenerate table
+    for (unsigned i = cdfnum; i < 256; i++) if (h[i]) bad = 1;
+    for (unsigned i = cdfnum + 1; i < (unsigned)CDF_STRIDE; i++) c[i] = 0;       // the unused tail of the 257-entry row is defined (it travels in the container)
     if (status) status[j] = bad ? -1 : 0;
 }
 

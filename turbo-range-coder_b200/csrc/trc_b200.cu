@@ -666,7 +666,7 @@ static const bool g_trace = getenv("TRC_TRACE") != nullptr;
 static int host_enc_pipelined(Ctx &c, int codec, const unsigned char *in, size_t total_len, size_t chunk_len, const cdf_t *cdf,
                               unsigned cdfnum, size_t cpc, unsigned char *out, uint64_t *out_off, size_t *out_len, size_t n, size_t gsz) {
     int rc;
-    const size_t nsub = (n + gsz - 1) / gsz, sub_len = gsz * chunk_len, stride = al256(sub_len + 512);
+    const size_t nsub = (n + gsz - 1) / gsz, sub_len = gsz * chunk_len, stride = al256(trc_enc_bound(sub_len, chunk_len));   // (rccdf4ienc answers 4 bytes on inputs shorter than 4)
     Plan p; rc = make_plan(codec, sub_len < total_len ? sub_len : total_len, chunk_len, p); if (rc) return rc;
     if ((rc = c.in.need(total_len + 64)) || (rc = c.out.need(nsub * stride)) || (rc = c.off.need((n + nsub + 1) * 8)) ||
         (rc = c.need_hoff(n + nsub + 1))) return rc;
@@ -1080,6 +1080,10 @@ int trc_container_info(const unsigned char *in, size_t in_len, int *codec, size_
     if (!in || in_len < CT_HDR) return TRC_E_ARG;
     CtHeader h; memcpy(&h, in, CT_HDR);
     if (h.magic != CT_MAGIC || h.version != 1 || h.codec >= NCODECS || h.total_len == 0 || h.chunk_len == 0) return TRC_E_ARG;
+    // untrusted sizes: bound them by what the buffer can possibly hold before any arithmetic on them (a chunk is at least one
+    // byte of payload or one directory entry; lengths are 32-bit per call)
+    if (h.chunk_len >= (1ull << 31) || h.total_len > (1ull << 48) || h.n_chunks > in_len / 4 || h.cdf_block > h.total_len + h.chunk_len ||
+        (h.total_len + h.chunk_len - 1) / h.chunk_len != h.n_chunks) return TRC_E_ARG;
     CtLayout L; if (ct_layout(h.codec, h.total_len, h.chunk_len, h.cdf_block, L) != TRC_OK) return TRC_E_ARG;
     if (h.n_chunks != L.n || h.n_tables != L.ntab || h.cdfnum != L.cdfnum) return TRC_E_ARG;
     if (L.off_payload > in_len || h.payload_bytes > in_len - L.off_payload) return TRC_E_ARG;
@@ -1109,8 +1113,9 @@ int trc_compress_host(int codec, const unsigned char *in, size_t total_len, size
     rc = trc_enc_batch_dev(codec, (const unsigned char *)c.in.p, total_len, chunk_len, (const cdf_t *)c.cdf.p, L.cdfnum, L.cpc,
                            (unsigned char *)c.out.p, (uint64_t *)c.off.p, c.scratch.p, c.scratch.cap, c.st);
     if (rc) return rc;
-    std::vector<uint64_t> off(L.n + 1);
-    std::vector<int> status(L.ntab);
+    std::vector<uint64_t> off;
+    std::vector<int> status;
+    try { off.resize(L.n + 1); status.resize(L.ntab); } catch (const std::bad_alloc &) { return TRC_E_NOMEM; }
     CK(cudaMemcpyAsync(off.data(), c.off.p, (L.n + 1) * 8, cudaMemcpyDeviceToHost, c.st));
     if (L.ntab) {
         CK(cudaMemcpyAsync(status.data(), c.status.p, L.ntab * sizeof(int), cudaMemcpyDeviceToHost, c.st));
@@ -1139,7 +1144,8 @@ int trc_decompress_host(const unsigned char *in, size_t in_len, unsigned char *o
     if (!out || out_cap < total_len) return TRC_E_NOMEM;
     CtHeader h; memcpy(&h, in, CT_HDR);
     CtLayout L; ct_layout(codec, total_len, chunk_len, h.cdf_block, L);
-    std::vector<uint64_t> off(n + 1);
+    std::vector<uint64_t> off;
+    try { off.resize(n + 1); } catch (const std::bad_alloc &) { return TRC_E_NOMEM; }   // never let an exception cross the C boundary
     const unsigned char *dirp = in + L.off_dir;
     off[0] = 0;
     for (size_t k = 0; k < n; k++) {
