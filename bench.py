@@ -49,7 +49,7 @@ REF_FN = {0: ("anscdf4senc", "anscdf4sdec"), 1: ("anscdf4enc", "anscdf4dec"), 2:
 CALLS_PER_SM = 384     # resident reference calls per SM in one wave of the lane-per-coder rcs2 kernels (2 CTAs x 192 calls x 2 lanes)
 B200_SMS = 148         # the default chunk is sized for this part; both arms derive it from the same constants (no device query)
 METRIC = "encode+decode GB/s on 100MB order-0 byte stream; bitstream bit-exact vs ref"
-SRC_NAME = {"zipf": "Zipf(1.1)", "bwt": "BWT-shaped", "o1": "order-1 Markov", "uniform": "uniform random"}
+SRC_NAME = {"zipf-dev": "Zipf(1.1) (generated on the device)", "zipf": "Zipf(1.1)", "bwt": "BWT-shaped", "o1": "order-1 Markov", "uniform": "uniform random"}
 
 
 def peaks():
@@ -136,6 +136,21 @@ def workload_config(args, chunk, world):
 def sha16(a):
     import hashlib
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def zipf_dev(torch, n, dev, seed):
+    """Zipf(1.1) bytes generated on the device (numpy needs ~85 s per GB): rank ~ Zipf over 256 symbols through a fixed random
+    permutation, like datagen.zipf, from torch's generator.  Deterministic for a given torch build."""
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    k = torch.arange(1, 257, dtype=torch.float64, device=dev)
+    cdf = torch.cumsum(k ** -1.1, 0); cdf = (cdf / cdf[-1]).to(torch.float32)
+    perm = torch.randperm(256, generator=g, device=dev).to(torch.uint8)
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    step = 1 << 26
+    for o in range(0, n, step):
+        m = min(step, n - o)
+        out[o:o + m] = perm[torch.searchsorted(cdf, torch.rand(m, generator=g, device=dev)).clamp_(max=255)]
+    return out
 
 
 def make_data(size, rank=0, src="zipf"):
@@ -313,7 +328,11 @@ def run_ours(args):
     size, chunk = args.size, default_chunk(args)
     static = codec in (0, 4, 5, 10)
 
-    data = make_data(size, rank, args.src)
+    if args.src == "zipf-dev":
+        d_in = zipf_dev(torch, size, dev, 20261017 + rank)
+        data = d_in.cpu().numpy()
+    else:
+        data = make_data(size, rank, args.src)
     if codec in (0, 1, 8, 9) and not (codec == 0 and args.bytes_alphabet):   # 16-symbol codecs get the low nibbles
         data = data & 15
     d_in = torch.from_numpy(data).to(dev)
@@ -619,7 +638,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="bytes per reference call; 0 = size the batch to one balanced wave (384 calls per SM: 1760 B for 100 MB on 148 SMs; DESIGN.md section 5)")
     ap.add_argument("--size", type=int, default=100_000_000)
     ap.add_argument("--bytes-alphabet", action="store_true", help="ans4s: code full bytes with a 256-entry table")
-    ap.add_argument("--src", default="zipf", choices=["zipf", "bwt", "o1", "uniform"], help="synthetic source (SURVEY.md section 8d)")
+    ap.add_argument("--src", default="zipf", choices=["zipf", "zipf-dev", "bwt", "o1", "uniform"], help="synthetic source (SURVEY.md section 8d)")
     ap.add_argument("--cdf-block", type=int, default=0, help="static codecs: one cdfini table per this many bytes (0 = whole buffer)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tables", action="store_true", help="rebuild the coding tables inside every call instead of using a prebuilt handle")
