@@ -511,7 +511,7 @@ def run_ours(args):
     h_off = torch.empty(n_chunks + 1, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
     h_back = torch.empty(size, dtype=torch.uint8).pin_memory().numpy()
     cdf_h = batch.cdf.cpu().numpy().view(np.uint16) if static else None
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = 1 if args.quick else max(3, min(args.steps, 10))
     te = td = 0.0
     for k in range(2 + e2e_steps):
         a = time.perf_counter()
@@ -642,10 +642,13 @@ def main():
     ap.add_argument("--cdf-block", type=int, default=0, help="static codecs: one cdfini table per this many bytes (0 = whole buffer)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tables", action="store_true", help="rebuild the coding tables inside every call instead of using a prebuilt handle")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only: skip the oracle gate, the e2e legs, the CPU baseline and the extras (sweeps)")
     ap.add_argument("--no-multi-e2e", action="store_true", help="N > 1: skip the single-process multi-device e2e leg")
     ap.add_argument("--no-gate", action="store_true", help="skip the oracle comparison of the packed stream (device round trip only)")
     ap.add_argument("--no-extras", action="store_true", help="skip the chunk sweep and the BASELINE config 3/4 lines (extra keys of the JSON line)")
     args = ap.parse_args()
+    if args.quick:
+        args.no_gate = args.no_cpu = args.no_extras = args.no_multi_e2e = True
     return run_reference(args) if args.impl == "reference" else run_ours(args)
 
 
