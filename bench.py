@@ -391,7 +391,7 @@ def run_ours(args):
         ok = torch.zeros(1, dtype=torch.int32, device=dev)
         if os.environ.get("TRC_GATHER", "peer") == "peer":
             try:
-                peer = shard.PeerGather(batch.out.numel(), dst=0, depth=2)
+                peer = shard.PeerGather(batch.out.numel(), dst=0, depth=int(os.environ.get("TRC_PEER_DEPTH", "2")))
                 ok += 1
             except Exception as e:                      # no peer access
                 print(f"[rank {rank}] PeerGather unavailable ({e})", file=sys.stderr)
@@ -404,7 +404,7 @@ def run_ours(args):
             if rank == 0:
                 gather_buf = torch.empty(int(size * 1.05) * world, dtype=torch.uint8, device=dev)
         else:
-            gather_kind = "peer-memory push (CUDA IPC over NVLink), device-driven: flags + acks, overlapped with decode and the next encode"
+            gather_kind = "peer-memory push (CUDA IPC over NVLink): copy engine for the predicted length (the previous size), device-side remainder + length + completion flag, acks for back-pressure; overlapped with decode and the next encode"
     side = torch.cuda.Stream(device=dev) if peer is not None else None
     ev_enc = torch.cuda.Event()
     ev_push = [torch.cuda.Event() for _ in range(NSETS)]
@@ -412,6 +412,8 @@ def run_ours(args):
         e.record()
     total_ptr = [bb.off.data_ptr() + 8 * bb.n for bb in sets]           # device address of out_off[n] = packed length
     state = {"k": 0, "seq": 0}
+
+    nogather = bool(os.environ.get("TRC_BENCH_NOGATHER"))      # experiments only: time the N ranks without any exchange
 
     def step(ev=None):
         main = torch.cuda.current_stream()
@@ -421,17 +423,17 @@ def run_ours(args):
         if peer is not None:
             main.wait_event(ev_push[ia])                 # the push that read this set's stream (three steps ago) is done
         sets[ia].encode(d_ins[ia])
-        if peer is not None:
+        if peer is not None and not nogather:
             ev_enc.record(main)
             side.wait_event(ev_enc)
             with torch.cuda.stream(side):
-                state["seq"] = peer.push(sets[ia].out, total_ptr[ia], side)
+                state["seq"] = peer.push(sets[ia].out, total_ptr[ia], side, hint_bytes=0 if os.environ.get("TRC_PUSH_NOHINT") else clen)
                 ev_push[ia].record(side)
         elif world > 1:
             shard.gather_compressed(sets[ia].out[:clen], dst=0, out=gather_buf)
         if ev: ev[1].record()
         sets[ib].decode()
-        if peer is not None and rank == 0 and state["seq"] >= 2:
+        if peer is not None and rank == 0 and state["seq"] >= 2 and not os.environ.get("TRC_BENCH_NOWAIT"):
             peer.wait_all(state["seq"] - 1, main)        # rank 0 holds every stream of the previous step ...
             peer.ack(state["seq"] - 1, main)             # ... and releases that slot set
 
@@ -458,6 +460,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     for k in range(args.steps):
         step(evs[k])
+    t_enq = time.perf_counter() - t0                     # host time to enqueue the steps (the GPU must not be waiting for it)
     finish()
     ev_end.record()
     torch.cuda.synchronize()
@@ -618,7 +621,7 @@ def run_ours(args):
             "enc_gbs": round(total_bytes / (enc_ms * 1e-3) / 1e9, 3), "dec_gbs": round(total_bytes / (dec_ms * 1e-3) / 1e9, 3),
             "ratio": round(clen / size, 5), "compressed_bytes": int(clen), "stream_sha16": stream_sha,
             "gate": "whole packed stream + offsets byte-compared with the oracle's at this chunk size" if stream_sha else "device round trip only (--no-gate)",
-            "wall_ms_per_step": round(wall / args.steps * 1e3, 4),
+            "wall_ms_per_step": round(wall / args.steps * 1e3, 4), "host_enqueue_ms_per_step": round(t_enq / args.steps * 1e3, 4),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
     if extras:
         line.update(extras)

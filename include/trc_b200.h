@@ -181,7 +181,7 @@ int trc_ipc_open(const unsigned char *handle64, void **p);
 int trc_ipc_close(void *p);
 int trc_memcpy_dev(void *dst, const void *src, size_t bytes, void *cuda_stream);
 int trc_push_dev(void *dst, const void *src, const uint64_t *d_len, size_t fixed_len, size_t cap, uint64_t *dst_len,
-                 uint64_t *dst_flag, uint64_t seq, unsigned int *d_counter, const uint64_t *ack, uint64_t ack_need, void *cuda_stream);
+                 uint64_t *dst_flag, uint64_t seq, unsigned int *d_counter, const uint64_t *ack, uint64_t ack_need, size_t skip, void *cuda_stream);
 int trc_ack_dev(uint64_t *ack, uint64_t seq, void *cuda_stream);
 int trc_wait_flags_dev(const uint64_t *flags, const uint64_t *lens, unsigned n, uint64_t seq, unsigned int *d_status, void *cuda_stream);
 

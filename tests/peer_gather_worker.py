@@ -38,7 +38,7 @@ def main():
         ev = torch.cuda.Event(); ev.record()
         side.wait_event(ev)
         with torch.cuda.stream(side):
-            seq = pg.push(b.out, total_ptr, side)
+            seq = pg.push(b.out, total_ptr, side, hint_bytes=(0, 1 << 20, 1 << 30)[step % 3])   # no hint / too short / too long
         assert seq == step
         if rank == 0:
             pg.wait_all(seq)                                  # device-side: the current stream continues only when all streams landed

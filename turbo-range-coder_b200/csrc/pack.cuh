@@ -111,21 +111,24 @@ __global__ void k_publish_u64(const uint64_t *__restrict__ src, uint64_t *__rest
 // publishes the length, fences again, and only then writes the sequence number into the destination's flag word.  The
 // consumer (k_wait_flags on the destination) spins on the flag with volatile loads: flag >= seq  =>  length and payload of
 // push `seq` have landed.  A stream longer than the slot is not copied beyond `cap`: the published length keeps the TRUE size
-// with its top bit set, which the consumer reports as an overflow.
+// with its top bit set, which the consumer reports as an overflow.  A caller that can predict the size (the previous step's, say)
+// lets a copy engine move that many bytes first (cudaMemcpyAsync on the same stream) and passes them as `skip`: the kernel then only
+// moves the remainder and publishes -- the SMs stay with the coders.
 constexpr unsigned long long PUSH_OVERFLOW = 1ull << 63;
 __global__ void __launch_bounds__(256)
 k_push(uint4 *__restrict__ dst, const uint4 *__restrict__ src, const uint64_t *__restrict__ d_len, size_t fixed_len, size_t cap,
        uint64_t *__restrict__ dst_len, volatile uint64_t *__restrict__ dst_flag, uint64_t seq, unsigned int *__restrict__ counter,
-       const volatile uint64_t *__restrict__ ack, uint64_t ack_need) {
+       const volatile uint64_t *__restrict__ ack, uint64_t ack_need, size_t skip) {
     // back-pressure: the slot may be overwritten only after the consumer acknowledged the push that used it last
     if (ack && threadIdx.x == 0) while (*ack < ack_need) __nanosleep(128);
     if (ack) __syncthreads();
     const uint64_t len = d_len ? *d_len : (uint64_t)fixed_len;
     const uint64_t clen = cap && len > cap ? cap : len;
+    // `skip` bytes (a multiple of 16) were already moved by a copy engine: only what lies beyond them is copied here
     const size_t nv = (size_t)((clen + 15) >> 4), stride = (size_t)gridDim.x * blockDim.x;
     // four 16-byte chunks in flight per thread: the kernel runs on a few CTAs next to the decoder, so the bandwidth over
     // NVLink has to come from memory-level parallelism per thread, not from thread count
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t i = (skip >> 4) + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + 3 * stride < nv; i += 4 * stride) {
         const uint4 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
         dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;

@@ -32,6 +32,7 @@ constexpr uint32_t E3_RING_S  = 4096;                   // bytes between consecu
 constexpr uint32_t E3_LEAD    = 6;                      // blocks a warp may run ahead of the slowest warp of its CTA (see the pacing note in k_rcs2_enc3)
 constexpr uint32_t E3_TILE_BYTES = 16 * 128;            // one input stage of a warp: 16 calls x 128 bytes
 constexpr int      E3_STAGES = 2;
+constexpr int      E3_COPY_U = 16;                     // words in flight per lane in the layout epilogue
 
 // {cdf, freq} of every symbol as one 8-byte entry (one LDS.64 per symbol, nothing to unpack)
 struct __align__(16) EncTab2 { uint2 e[256]; };
@@ -126,7 +127,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 // g.chunk is a multiple of 16.  The tensor map covers the FULL calls only (a shorter last call would make TMA read past the
 // end of the caller's buffer): the two lanes of a short last call load their bytes directly and run the generic remainder.
 template <bool TMA>
-__global__ void __launch_bounds__(E3_MAX_NT, 1)
+__global__ void __maxnreg__(64)
 k_rcs2_enc3(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ in, Geom g, size_t n_calls,
             const EncTab2 *__restrict__ tab, uint8_t *__restrict__ slots, size_t slot_stride, unsigned calls_per_cta,
             volatile unsigned long long *__restrict__ lb, uint64_t *__restrict__ out_off, uint8_t *__restrict__ out, unsigned flags) {
@@ -389,12 +390,12 @@ k_rcs2_enc3(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict_
             const uint32_t *pa = (const uint32_t *)sl, *pb = (const uint32_t *)(sl + s_boff[q]);
             const uint32_t wa = s_alen[q] >> 2, W = wa + (s_blen[q] >> 2), len0 = s_alen[q] - 4;   // word 0 = the len0 header (rccdf.c:141)
             uint32_t *d = (uint32_t *)dst;
-            for (uint32_t w0 = 0; w0 < W; w0 += LB_U * 8) {
-                uint32_t vv[LB_U];
+            for (uint32_t w0 = 0; w0 < W; w0 += E3_COPY_U * 8) {
+                uint32_t vv[E3_COPY_U];
 #pragma unroll
-                for (int k = 0; k < LB_U; k++) { const uint32_t w = w0 + k * 8 + sub; vv[k] = w == 0 ? len0 : (w < wa ? pa[w] : (w < W ? pb[w - wa] : 0u)); }
+                for (int k = 0; k < E3_COPY_U; k++) { const uint32_t w = w0 + k * 8 + sub; vv[k] = w == 0 ? len0 : (w < wa ? pa[w] : (w < W ? pb[w - wa] : 0u)); }
 #pragma unroll
-                for (int k = 0; k < LB_U; k++) { const uint32_t w = w0 + k * 8 + sub; if (w < W) __stcs(d + w, vv[k]); }
+                for (int k = 0; k < E3_COPY_U; k++) { const uint32_t w = w0 + k * 8 + sub; if (w < W) __stcs(d + w, vv[k]); }
             }
         } else {
             if (sub == 0) *(uint32_t *)sl = s_alen[q] - 4;

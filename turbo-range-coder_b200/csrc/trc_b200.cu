@@ -157,6 +157,16 @@ static int dev_attrs() {
     CK(cudaFuncSetAttribute(k_rcs2_enc3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem_bytes(E3_MAX_NT, true)));
     CK(cudaFuncSetAttribute(k_rcs2_enc3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e3_smem_bytes(E3_MAX_NT, false)));
     CK(cudaFuncSetAttribute(k_rcs2_dec3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D3_SMEM));
+    // The shared-memory / L1 split is an SM-wide setting: a resident CTA of a kernel that asked for a different split keeps the
+    // SM from being reconfigured, and the coder CTAs queued behind it wait.  The small helper kernels that run NEXT TO the coders
+    // (peer push, flag wait, acknowledgement) use no shared memory and would pull the split towards L1: they ask for the coders'
+    // split instead (k_rcs2_enc3: one 142 KB CTA, k_rcs2_dec3: two 68 KB CTAs per SM -> the 164 KB setting = 72 % of 228 KB).
+    const int carve = getenv("TRC_PUSH_CARVEOUT") ? atoi(getenv("TRC_PUSH_CARVEOUT")) : 72;
+    if (carve >= 0) {
+        CK(cudaFuncSetAttribute(k_push, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        CK(cudaFuncSetAttribute(k_wait_flags, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+        CK(cudaFuncSetAttribute(k_ack, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    }
     CK(cudaFuncSetAttribute(k_rcs2_dec_lpc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RING_W * LPC_MAX_NT * sizeof(uint32_t))));
     CK(cudaFuncSetAttribute(k_rans_static_dec_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RING_W * LPC_MAX_NT * sizeof(uint32_t))));
     CK(cudaFuncSetAttribute(k_ans_model3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m3_warp_bytes<true>()));
@@ -566,11 +576,14 @@ int trc_memcpy_dev(void *dst, const void *src, size_t bytes, void *cuda_stream) 
 // the length at dst_len and `seq` at dst_flag (see k_push for the completion protocol).  d_counter: one zeroed uint32 in LOCAL
 // device memory per concurrent push (NULL only with dst_flag == NULL: length published without a completion guarantee).
 // ack / ack_need (optional): do not touch dst before *ack >= ack_need (the consumer's acknowledgement of the push that used the slot last).
+// skip: bytes at the front of the stream that a copy engine already moved (stream-ordered before this call); 0 = copy everything here.
 int trc_push_dev(void *dst, const void *src, const uint64_t *d_len, size_t fixed_len, size_t cap, uint64_t *dst_len,
-                 uint64_t *dst_flag, uint64_t seq, unsigned int *d_counter, const uint64_t *ack, uint64_t ack_need, void *cuda_stream) {
-    if (!dst || !src || (((uintptr_t)dst | (uintptr_t)src) & 15) || (dst_flag && !d_counter)) return TRC_E_ARG;
-    static const int ctas = getenv("TRC_PUSH_CTAS") ? atoi(getenv("TRC_PUSH_CTAS")) : 32;   // few CTAs: enough stores in flight for NVLink, little SM time stolen from the coders
-    k_push<<<ctas, 256, 0, (cudaStream_t)cuda_stream>>>((uint4 *)dst, (const uint4 *)src, d_len, fixed_len, cap, dst_len, dst_flag, seq, d_counter, ack, ack_need);
+                 uint64_t *dst_flag, uint64_t seq, unsigned int *d_counter, const uint64_t *ack, uint64_t ack_need, size_t skip, void *cuda_stream) {
+    if (!dst || !src || (((uintptr_t)dst | (uintptr_t)src) & 15) || (dst_flag && !d_counter) || (skip & 15) || (cap && skip > cap)) return TRC_E_ARG;
+    { int rc0 = dev_attrs(); if (rc0) return rc0; }
+    static const int ctas_full = getenv("TRC_PUSH_CTAS") ? atoi(getenv("TRC_PUSH_CTAS")) : 32;
+    const int ctas = skip ? 4 : ctas_full;                            // a remainder behind a copy-engine transfer is small   // few CTAs: enough stores in flight for NVLink, little SM time stolen from the coders
+    k_push<<<ctas, 256, 0, (cudaStream_t)cuda_stream>>>((uint4 *)dst, (const uint4 *)src, d_len, fixed_len, cap, dst_len, dst_flag, seq, d_counter, ack, ack_need, skip);
     CK_LAUNCH();
     return TRC_OK;
 }

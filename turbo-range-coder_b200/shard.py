@@ -113,18 +113,29 @@ class PeerGather:
         d = (self.seq if seq is None else seq) % self.depth
         return self.base.value + self.off_flags + 8 * self._slot(d, r)
 
-    def push(self, payload: torch.Tensor, d_len_ptr: int, stream=None) -> int:
+    def push(self, payload: torch.Tensor, d_len_ptr: int, stream=None, hint_bytes: int = 0) -> int:
         """payload: the local packed stream buffer (16-byte aligned); d_len_ptr: device address of its uint64 length.
+        hint_bytes: a prediction of the length known on the host (the previous step's, say; 0 = none): that many bytes travel by
+        copy engine (cudaMemcpyAsync to the peer mapping) and the kernel only moves what lies beyond them and publishes, so the SMs
+        stay with the coders.  A wrong hint costs bandwidth (too long) or SM time (too short), never correctness.
         Returns the sequence number of this push (1, 2, ...): the same number on every rank names the same step."""
         st = stream if stream is not None else torch.cuda.current_stream()
         self.seq += 1
-        s, ct = self.seq, self.ct
-        rc = self.trc.lib.trc_push_dev(ct.c_void_p(self.slot_ptr(self.rank, s)), ct.c_void_p(payload.data_ptr()), ct.c_void_p(d_len_ptr),
-                                       ct.c_size_t(0), ct.c_size_t(self.slot_bytes), ct.c_void_p(self.len_ptr(self.rank, s)),
-                                       ct.c_void_p(self.flag_ptr(self.rank, s)), ct.c_uint64(s),
-                                       ct.c_void_p(self.local.value + 4 * (s % self.depth)),
-                                       ct.c_void_p(self.base.value + self.off_ack + 8 * (s % self.depth)), ct.c_uint64(max(0, s - self.depth)),
-                                       ct.c_void_p(st.cuda_stream))
+        s, ct, lib = self.seq, self.ct, self.trc.lib
+        ack = self.base.value + self.off_ack + 8 * (s % self.depth)
+        need = max(0, s - self.depth)
+        skip = min(int(hint_bytes), self.slot_bytes, payload.numel()) & ~15
+        if skip:
+            if need:                                          # the slot must be free before the copy engine touches it
+                self.trc._check(lib.trc_wait_flags_dev(ct.c_void_p(ack), None, ct.c_uint(1), ct.c_uint64(need), None, ct.c_void_p(st.cuda_stream)),
+                                "trc_wait_flags_dev (ack)")
+            self.trc._check(lib.trc_memcpy_dev(ct.c_void_p(self.slot_ptr(self.rank, s)), ct.c_void_p(payload.data_ptr()), ct.c_size_t(skip),
+                                               ct.c_void_p(st.cuda_stream)), "trc_memcpy_dev")
+        rc = lib.trc_push_dev(ct.c_void_p(self.slot_ptr(self.rank, s)), ct.c_void_p(payload.data_ptr()), ct.c_void_p(d_len_ptr),
+                              ct.c_size_t(0), ct.c_size_t(self.slot_bytes), ct.c_void_p(self.len_ptr(self.rank, s)),
+                              ct.c_void_p(self.flag_ptr(self.rank, s)), ct.c_uint64(s),
+                              ct.c_void_p(self.local.value + 4 * (s % self.depth)),
+                              None if skip else ct.c_void_p(ack), ct.c_uint64(need), ct.c_size_t(skip), ct.c_void_p(st.cuda_stream))
         self.trc._check(rc, "trc_push_dev")
         return s
 
@@ -155,7 +166,7 @@ class PeerGather:
         ct = self.ct
         rc = self.trc.lib.trc_push_dev(ct.c_void_p(out.data_ptr()), ct.c_void_p(self.slot_ptr(r, seq)), ct.c_void_p(self.len_ptr(r, seq)),
                                        ct.c_size_t(0), ct.c_size_t(out.numel() & ~15), None, None, ct.c_uint64(0), None, None, ct.c_uint64(0),
-                                       ct.c_void_p(st.cuda_stream))
+                                       ct.c_size_t(0), ct.c_void_p(st.cuda_stream))
         self.trc._check(rc, "trc_push_dev (fetch)")
 
     def read_slot(self, r, nbytes, device, seq=None):
