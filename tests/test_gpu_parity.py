@@ -368,3 +368,16 @@ def test_rcs2_ab_switches(port, dg):
     for var in ({}, {"TRC_ENC_TMA": "0"}, {"TRC_DEC3": "0"}, {"TRC_FUSED": "0"}):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **var), timeout=900)
         assert r.returncode == 0 and "ab ok" in r.stdout, (var, r.stdout[-2000:] + r.stderr[-2000:])
+
+
+def test_order1_many_calls(trc, port, sources, dg):
+    """TRC_ANS1 with hundreds of calls takes the half-warp-per-call decoder whose low-nibble tables live in global memory
+    (k_ans1_dec_g); it must decode the oracle's streams byte for byte -- ragged last call, an odd number of calls, raw calls."""
+    for name, n, chunk in (("o1", 3_100_003, 4096), ("bwt", 1_600_000, 2048), ("uniform", 800_000, 1024), ("zipf", 6_100_000, 8192 + 1)):
+        d = (dg.markov1(n) if name == "o1" else dg.bwt_shaped(n) if name == "bwt" else dg.uniform(n) if name == "uniform" else dg.zipf(n))
+        assert trc.num_chunks(n, chunk) >= 5 * 148
+        want, woff = cpu_batch(port, trc.ANS1, d, chunk)
+        got, off = trc.enc_batch_host(trc.ANS1, d, chunk)
+        assert np.array_equal(off, woff) and np.array_equal(got, want), (name, chunk)
+        back = trc.dec_batch_host(trc.ANS1, want, woff, n, chunk)
+        assert np.array_equal(back, d), (name, chunk, first_diff(back, d))

@@ -434,6 +434,129 @@ k_ans_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, 
 }
 
 // ================================================================================================================
+// Order-1 decoder for batches of MANY calls (TRC_ANS1, anscdf1dec anscdf.c:629-645): one HALF-warp per call like the order-0
+// decoder, so an SM runs 24 calls at once instead of one.  What made k_ans_dec3<true> a one-call-per-SM kernel is the 136 KB
+// of low-nibble tables mbl[256][16][17]; here only the high-nibble tables mbh[256][16] (8 KB) live in shared memory and the
+// low-nibble tables live in GLOBAL memory (128 KB per resident call, L1/L2 resident: the rows a call keeps returning to stay
+// in L1).  A lane only ever reads and writes ITS OWN entry of every table row, so program order alone keeps the tables
+// coherent -- no fences, no warp synchronisation around the table traffic.  The row fetch (an L1 or L2 hit) sits on the
+// per-byte chain of a call (measured ~860 cycles per byte and call against ~200 with the tables in shared memory; prefetching
+// the 16 candidate rows of the next context into L1 did not help: the call's own stores keep evicting them), so the kernel wins
+// from about five calls per SM upwards.  Same bytes as k_ans_dec3<true>.
+// ================================================================================================================
+constexpr int G1_WPB = 4;                                         // warps per CTA: 8 calls
+constexpr uint32_t G1_MBH_BYTES = 256u * 16u * 2u;                // high-nibble tables of one call
+constexpr uint32_t G1_MBL_ENTRIES = 256u * 16u * 16u;             // low-nibble tables of one call (global memory)
+constexpr uint32_t G1_SMEM = G1_WPB * 2u * (G1_MBH_BYTES + D3_RING_BYTES);
+
+__global__ void __launch_bounds__(G1_WPB * 32)
+k_ans1_dec_g(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off, uint8_t *__restrict__ out, Geom g, uint16_t *__restrict__ mbl_all) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5, i = lane & 15, hb = lane & 16, half = lane >> 4;
+    uint8_t *sb = smem_raw + (size_t)(wib * 2 + half) * (G1_MBH_BYTES + D3_RING_BYTES);
+    uint16_t *Th = (uint16_t *)sb, *ring = (uint16_t *)(sb + G1_MBH_BYTES);
+    uint32_t *ring32 = (uint32_t *)ring;
+    const unsigned hm = 0xffffu << hb, hbm1 = hb - 1;
+    const int c10 = ADAPT_IC_ * (int)i, c10mix = c10 + (int)AD_MIX;
+    const size_t nwarps = (size_t)gridDim.x * G1_WPB, gw = (size_t)blockIdx.x * G1_WPB + wib;
+    uint16_t *G = mbl_all + (gw * 2 + half) * (size_t)G1_MBL_ENTRIES + i;     // this lane's entry of row 0
+    uint16_t *Thi = Th + i;
+    const uint8_t *gend = in + in_off[g.n_calls];
+    const bool writer = i < 4;
+    for (size_t jb = gw * 2; jb < g.n_calls; jb += nwarps * 2) {
+        const size_t j = jb + half;
+        bool act = j < g.n_calls;
+        size_t start = 0, len = 0; uint64_t so = 0, sl = 0;
+        if (act) { call_span(g, j, start, len); so = in_off[j]; sl = in_off[j + 1] - so; }
+        uint8_t *op = out + start;
+        if (act && sl == len) { group_copy(op, in + so, len, i, 16); act = false; }     // raw chunk (CCPY turborc.c:434)
+        const uint32_t nblk = act ? (uint32_t)((len + ANS_BLOCK - 1) / ANS_BLOCK) : 0u;
+        const uint32_t nblk_o = __shfl_xor_sync(FULLMASK, nblk, 16), nblk_max = nblk > nblk_o ? nblk : nblk_o;
+        const uint8_t *sp = act ? in + so : gend;
+        uint32_t hp = 0, hf = 32;                                 // halfwords consumed / staged (see k_ans_dec3)
+        __syncwarp();
+        { const uint32_t v = ld32_any(sp + 4 * i, gend); ring32[i] = v; if (i < 2) ring32[32 + i] = v; }
+        uint32_t pend = ld32_any(sp + 64 + 4 * i, gend);
+        __syncwarp();
+        auto refill = [&]() {
+            const bool need = hf - hp <= 32;
+            if (__any_sync(FULLMASK, need)) {
+                __syncwarp();
+                if (need) {
+                    const uint32_t wb = (hf >> 1) & 31;
+                    ring32[wb + i] = pend;
+                    if (wb == 0 && i < 2) ring32[32 + i] = pend;
+                    hf += 32;
+                    pend = ld32_any(sp + 2 * (size_t)hf + 4 * i, gend);
+                }
+                __syncwarp();
+            }
+        };
+        uint32_t cx = 0;                                          // not reset per block (anscdf.c:629)
+        for (uint32_t b = 0; b < nblk_max; b++) {
+            const bool bact = act && b < nblk;
+            const size_t bpos = (size_t)b * ANS_BLOCK;
+            const uint32_t n = bact ? (uint32_t)(len - bpos < ANS_BLOCK ? len - bpos : ANS_BLOCK) : 0u, npairs = (n + 1) >> 1;
+            const uint32_t np_o = __shfl_xor_sync(FULLMASK, npairs, 16), npmax = npairs > np_o ? npairs : np_o;
+            uint8_t *bo = op + bpos;
+            if (bact) {                                           // CDF16DEC1 / CDF16DEC2 cdf_.h:28-32: every table = { j << 11 }
+                const uint16_t v0 = (uint16_t)(i << 11);
+                for (uint32_t k = 0; k < 256u * 16u; k += 16) Thi[k] = v0;
+                // low-nibble tables: 128 KB of the same 32-byte row; 16 lanes x 16 bytes per step
+                const uint32_t e0 = (i & 1) * 8;                  // first entry of this lane's 16-byte piece of a row
+                const uint4 pat = make_uint4(((e0 + 1) << 27) | (e0 << 11), ((e0 + 3) << 27) | ((e0 + 2) << 11), ((e0 + 5) << 27) | ((e0 + 4) << 11), ((e0 + 7) << 27) | ((e0 + 6) << 11));
+                uint4 *gp = (uint4 *)(G - i) + i;
+                for (uint32_t k = 0; k < G1_MBL_ENTRIES / 8; k += 16) gp[k] = pat;
+            }
+            __syncwarp();
+            refill();
+            uint32_t s0 = ANS_L, s1 = ANS_L, s2 = ANS_L, s3 = ANS_L;
+            if (bact) {                                           // mnfill anscdf_.h:176
+                auto hw = [&](uint32_t q) -> uint32_t { return ring[(hp + q) & (D3_RING - 1)]; };
+                s0 = hw(0) | hw(1) << 16; s1 = hw(2) | hw(3) << 16; s2 = hw(4) | hw(5) << 16; s3 = hw(6) | hw(7) << 16;
+                hp += 8;
+            }
+            auto nib_r = [&](uint32_t &st, int &m) -> uint32_t {  // next entry by shuffle inside the half-warp
+                const int dn = __shfl_down_sync(FULLMASK, m, 1, 16);
+                return d3_nib(st, m, i == 15 ? (int)PROB_TOTAL : dn, hbm1, hm, c10, c10mix);
+            };
+            auto nib_s = [&](uint32_t &st, uint16_t *e) -> uint32_t { int m = e[0]; const uint32_t c = nib_r(st, m); e[0] = (uint16_t)m; return c; };
+            auto nib_g = [&](uint32_t &st, uint16_t *e) -> uint32_t {
+                int m = bact ? (int)*e : (int)(i << 11);          // (an idle half keeps the shuffles company)
+                const uint32_t c = nib_r(st, m);
+                if (bact) *e = (uint16_t)m;
+                return c;
+            };
+            for (uint32_t pi = 0; pi < npmax; pi += 2) {          // two byte pairs per trip (mndec8x2x anscdf_.h:164-174)
+                refill();
+                uint32_t w = 0;
+#pragma unroll
+                for (int sub = 0; sub < 2; sub++) {
+                    const bool pact = pi + sub < npairs;
+                    const uint32_t h0 = nib_s(s0, Thi + cx * 16);
+                    const uint32_t q0 = nib_g(s1, G + ((cx * 16 + h0 - 1) << 4));
+                    const uint32_t x0 = (h0 * 16 + q0 - 17) & 0xffu;
+                    const uint32_t h1 = nib_s(s2, Thi + x0 * 16);
+                    const uint32_t q1 = nib_g(s3, G + ((x0 * 16 + h1 - 1) << 4));
+                    const uint32_t x1 = (h1 * 16 + q1 - 17) & 0xffu;
+                    cx = x1;
+                    const uint16_t *rp = ring + (hp & (D3_RING - 1));
+                    uint32_t cnt = 0;
+                    { const bool p = pact && s0 < ANS_L; const uint32_t v = rp[cnt]; s0 = p ? (s0 << 16 | v) : s0; cnt += p; }
+                    { const bool p = pact && s1 < ANS_L; const uint32_t v = rp[cnt]; s1 = p ? (s1 << 16 | v) : s1; cnt += p; }
+                    { const bool p = pact && s2 < ANS_L; const uint32_t v = rp[cnt]; s2 = p ? (s2 << 16 | v) : s2; cnt += p; }
+                    { const bool p = pact && s3 < ANS_L; const uint32_t v = rp[cnt]; s3 = p ? (s3 << 16 | v) : s3; cnt += p; }
+                    hp += cnt;
+                    w |= (x0 | x1 << 8) << (16 * sub);
+                }
+                const uint32_t o = 2 * pi + (lane & 3);
+                if (writer && o < n) bo[o] = (uint8_t)(w >> (8 * (lane & 3)));
+            }
+        }
+    }
+}
+
+// ================================================================================================================
 // adaptive byte RANGE decoders TRC_RC (rccdfdec rccdf.c:187-200) and TRC_RCI (rccdfidec rccdf.c:213-228), same mapping as
 // k_ans_dec3<false>: one HALF-warp per call, one CDF entry per lane, the high-nibble table in a register.
 //   * _cdflget16 (turborc_.h:271-291: first entry with cdf[e+1] * range > code) = one 47 x 15-bit multiply-compare per lane +

@@ -172,6 +172,7 @@ static int dev_attrs() {
     CK(cudaFuncSetAttribute(k_ans_model3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m3_warp_bytes<true>()));
     CK(cudaFuncSetAttribute(k_ans_code3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C3_LUT_BYTES));
     CK(cudaFuncSetAttribute(k_ans_dec3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d3_smem_bytes<true>()));
+    CK(cudaFuncSetAttribute(k_ans1_dec_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G1_SMEM));
     done[d] = true;
     return TRC_OK;
 }
@@ -505,9 +506,26 @@ static int dec_batch_impl(int codec, const unsigned char *d_in, const uint64_t *
     case ANS:   if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rans_adapt_dec<M_BYTE, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g, nullptr, flags);
                 else k_ans_dec3<false><<<blocks(g.n_calls, 2 * D3_WPB), D3_WPB * 32, d3_smem_bytes<false>(), st>>>(d_in, d_in_off, d_out, g);
                 break;
-    case ANS1:  rc = dev_attrs(); if (rc) return rc;
-                k_ans_dec3<true><<<(unsigned)(g.n_calls < (size_t)sm_count() ? g.n_calls : (size_t)sm_count()), 32, d3_smem_bytes<true>(), st>>>(d_in, d_in_off, d_out, g);
-                break;
+    case ANS1: {
+        rc = dev_attrs(); if (rc) return rc;
+        static const int g_o1g = getenv("TRC_O1_GLOBAL") ? atoi(getenv("TRC_O1_GLOBAL")) : 1;   // 0: always the one-call-per-SM kernel (A/B runs)
+        if (g_o1g && g.n_calls >= 5 * (size_t)sm_count()) {               // many calls: half-warp per call, low-nibble tables in global memory
+            // (one call per SM runs a byte in ~200 cycles, this kernel in ~860 but with every call at once: break-even ~4.3 calls per SM)
+            rc = pool_keep(); if (rc) return rc;
+            const size_t want = (g.n_calls + 2 * G1_WPB - 1) / (2 * G1_WPB), cap = (size_t)sm_count() * 3;
+            const unsigned ctas = (unsigned)(want < cap ? want : cap);
+            uint16_t *mbl = nullptr;
+            CK(cudaMallocAsync((void **)&mbl, (size_t)ctas * 2 * G1_WPB * G1_MBL_ENTRIES * sizeof(uint16_t), st));
+            k_ans1_dec_g<<<ctas, G1_WPB * 32, G1_SMEM, st>>>(d_in, d_in_off, d_out, g, mbl);
+            g_launches++; prof_mark(st);
+            cudaError_t e = cudaPeekAtLastError();
+            cudaFreeAsync(mbl, st);
+            CK(e);
+            return TRC_OK;
+        }
+        k_ans_dec3<true><<<(unsigned)(g.n_calls < (size_t)sm_count() ? g.n_calls : (size_t)sm_count()), 32, d3_smem_bytes<true>(), st>>>(d_in, d_in_off, d_out, g);
+        break;
+    }
     case RC:    if (g.n_calls >= COOP_MIN_LANE_UNITS) k_rc_adapt_dec<R_BYTE1, AD_NT_BYTE><<<blocks(g.n_calls, AD_NT_BYTE), AD_NT_BYTE, 0, st>>>(d_in, d_in_off, d_out, g);
                 else k_rc_dec3<1><<<blocks(g.n_calls, 2 * D3_WPB), D3_WPB * 32, r3_smem_bytes<1>(), st>>>(d_in, d_in_off, d_out, g);
                 break;
