@@ -394,7 +394,10 @@ def run_ours(args):
         ok = torch.zeros(1, dtype=torch.int32, device=dev)
         if os.environ.get("TRC_GATHER", "peer") == "peer":
             try:
-                peer = shard.PeerGather(batch.out.numel(), dst=0, depth=int(os.environ.get("TRC_PEER_DEPTH", "2")))
+                # slot sets on rank 0: enough of them that the sources are never held back by acknowledgements while the NVLink
+                # ingress of rank 0 (the bottleneck of an all-to-one gather) is busy; at most ~8 GiB of rank 0's memory
+                depth = int(os.environ.get("TRC_PEER_DEPTH", "0")) or max(2, min(8, (8 << 30) // (world * batch.out.numel())))
+                peer = shard.PeerGather(batch.out.numel(), dst=0, depth=depth)
                 ok += 1
             except Exception as e:                      # no peer access
                 print(f"[rank {rank}] PeerGather unavailable ({e})", file=sys.stderr)
