@@ -381,3 +381,37 @@ def test_order1_many_calls(trc, port, sources, dg):
         assert np.array_equal(off, woff) and np.array_equal(got, want), (name, chunk)
         back = trc.dec_batch_host(trc.ANS1, want, woff, n, chunk)
         assert np.array_equal(back, d), (name, chunk, first_diff(back, d))
+
+
+def test_rcs2_extreme_tables(trc, port, dg):
+    """TRC_RCS2 (lane-per-coder kernels) with tables that are NOT the data's own: many frequency-1 symbols (15 bits per symbol: the
+    most words a block can emit, streams that expand until the raw rule fires mid-chunk), two-symbol alphabets (frequency 32767: almost
+    no output, long stretches without renormalisation), mismatched skew -- every call against the oracle, encode and decode."""
+    rng = np.random.default_rng(77)
+    n = 600_000 + 112
+    cases = []
+    # (a) uniform table over 256 symbols, skewed data and the reverse
+    flat = (np.arange(257) * 128).astype(np.uint16)
+    cases.append(("flat table / zipf data", flat, 256, dg.zipf(n, seed=31)))
+    z = dg.zipf(n, seed=32)
+    cases.append(("zipf table / uniform data", port.cdfini(z), 256, dg.uniform(n, seed=33)))
+    # (b) 200 symbols of frequency 1, the rest shares 32768 - 200; data lives on the rare symbols half of the time
+    f = np.ones(256, np.int64); f[200:] = 0; rest = 32768 - 200
+    f[200:] = rest // 56; f[255] += rest - 56 * (rest // 56)
+    rare = np.concatenate([[0], np.cumsum(f)]).astype(np.uint16)
+    d = np.where(rng.random(n) < 0.5, rng.integers(0, 200, n), rng.integers(200, 256, n)).astype(np.uint8)
+    cases.append(("rare symbols", rare, 256, d))
+    cases.append(("rare symbols only", rare, 256, rng.integers(0, 200, n).astype(np.uint8)))
+    # (c) two symbols, 32767 : 1
+    two = np.zeros(257, np.uint16); two[1] = 32767; two[2] = 32768
+    d2 = (rng.random(n) < 0.001).astype(np.uint8)
+    cases.append(("two symbols", two, 2, d2))
+    cases.append(("two symbols, all zero", two, 2, np.zeros(n, np.uint8)))
+    for name, cdf, num, data in cases:
+        for chunk in (1760, 4096, 48, 65536):
+            want, woff = cpu_batch(port, trc.RCS2, data, chunk, cdf, num)
+            got, off = trc.enc_batch_host(trc.RCS2, data, chunk, cdf=cdf, cdfnum=num)
+            assert np.array_equal(off, woff), (name, chunk, first_diff(off, woff))
+            assert np.array_equal(got, want), (name, chunk, first_diff(got, want))
+            back = trc.dec_batch_host(trc.RCS2, got, off, data.size, chunk, cdf=cdf, cdfnum=num)
+            assert np.array_equal(back, data), (name, chunk, first_diff(back, data))
