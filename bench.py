@@ -300,7 +300,8 @@ def run_extras(trc, torch, dev, d_zipf, cdf_dev, flush, main_chunk):
                 "roofline_frac": round((n + clen) / (max(e, d) * 1e-3) / 1e9 / peaks()[0], 5)}
 
     bwt = torch.from_numpy(make_data(size, 0, "bwt")).to(dev)
-    out["config3_adaptive_bwt_100mb"] = [adaptive("rc", bwt, 65536, 3, "BWT-shaped bytes"), adaptive("ans", bwt, 65536, 3, "BWT-shaped bytes")]
+    # 64 KiB = SURVEY's default batch chunk; the smaller chunks show what more concurrent calls buy (and cost in ratio)
+    out["config3_adaptive_bwt_100mb"] = [adaptive(c, bwt, ck, 3, "BWT-shaped bytes") for ck in (65536, 16384, 4096) for c in ("rc", "ans")]
     del bwt
     o1 = markov1_dev(torch, 1_000_000_000, dev)
     # 4 MiB = the reference's own block size (one call per SM: 239 calls in two waves); 1 MiB chunks (954 calls) take the

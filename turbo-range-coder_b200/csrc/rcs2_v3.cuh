@@ -490,6 +490,9 @@ k_rcs2_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
     __shared__ uint64_t bar;
     const size_t j0 = (size_t)blockIdx.x * calls_per_cta, j = j0 + (threadIdx.x >> 1);
     const unsigned c = threadIdx.x & 1;
+    unsigned long long *tp = g_e3_times ? g_e3_times + ((size_t)blockIdx.x * 32 + (threadIdx.x >> 5)) * 8 : nullptr;   // phase probe (tools/enc_phases.py --dec)
+    const unsigned lane = threadIdx.x & 31;
+    E3_STAMP(0);
     if (threadIdx.x == 0) tma_fetch(tabs, ts + (cpc ? j0 / cpc : 0), (uint32_t)sizeof(DecTab2), &bar);
     __syncthreads();
     tma_wait(&bar);
@@ -572,6 +575,7 @@ k_rcs2_dec3(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
             *(uint2 *)(op + i + 8 * c) = v;
         }
     }
+    E3_STAMP(2);
     // remaining full pairs, then the odd tail on coder 0 (rccdf.c:179-182): exact path
     if (n > nb) {
         RcDExact ex;
