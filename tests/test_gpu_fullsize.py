@@ -62,6 +62,26 @@ def test_headline_chunks_100mb(trc, port, zipf100, chunk):
     assert _sha(back) == "e9e9669ae62e03c9"
 
 
+@pytest.mark.parametrize("chunk", [1328, 880, 512, 256])
+def test_rcs2_launch_shapes_100mb(trc, port, zipf100, chunk):
+    """Device-resident 100 MB in ONE batch, so that the kernels see every launch shape of trc_b200.cu's e3_shape / lpc_shape:
+    one 1024-thread CTA per SM (1328-byte chunks: 509 calls per SM), two / three / six balanced waves of two CTAs per SM
+    (880, 512, 256).  Packed stream, offsets and round trip against the oracle."""
+    import torch
+    t = torch.from_numpy(zipf100).cuda()
+    b = trc.DeviceBatch(trc.RCS2, N, chunk, cdfnum=256)
+    b.set_cdf(trc.cdfini(zipf100))
+    b.prebuild_tables()
+    b.encode(t); torch.cuda.synchronize()
+    n = b.compressed_len()
+    want, woff = _oracle_batch(port, trc.RCS2, zipf100, chunk, trc.cdfini(zipf100), 256)
+    assert n == want.size
+    assert np.array_equal(b.off.cpu().numpy().view(np.uint64), woff)
+    assert np.array_equal(b.out[:n].cpu().numpy(), want)
+    assert torch.equal(b.decode()[:N], t)
+    b.drop_tables()
+
+
 def test_config3_adaptive_100mb(trc, port, dg):
     """BASELINE config 3: 100 MB BWT-shaped stream through the adaptive byte rANS (-e56) and RC (-e46), 64 KiB chunks."""
     b = dg.bwt_shaped(N)

@@ -25,7 +25,7 @@
 
 namespace trc {
 
-constexpr int      E3_MAX_NT  = 768;                    // one CTA per SM: 384 calls, 24 warps
+constexpr int      E3_MAX_NT  = 1024;                   // one CTA per SM: up to 512 calls, 32 warps (64 registers per thread = the whole register file)
 constexpr int      E3_RING_W  = 8;                      // ring words per lane (<= 3 left over + <= 4 new per 8-symbol block)
 constexpr uint32_t E3_RING_S  = 4096;                   // bytes between consecutive ring words of a lane (room for 1024 lanes; a power of two so that the
                                                         // ring address is ONE shift-and-add of the cursor)

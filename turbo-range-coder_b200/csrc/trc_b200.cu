@@ -86,21 +86,40 @@ struct Plan {
 static inline size_t n_tables(size_t n_calls, size_t cpc) { return cpc ? (n_calls + cpc - 1) / cpc : 1; }
 // the throughput kernels (static_v2.cuh) need 16-byte aligned calls and table groups that do not split a CTA
 // lane-per-coder launch shape: (calls per CTA, CTAs).  Batches that fit one wave get one equally loaded CTA per SM.
-static void lpc_shape(size_t n_calls, size_t cpc, unsigned &calls_per_cta, unsigned &ctas) {
+static void lpc_shape(size_t n_calls, size_t cpc, unsigned &calls_per_cta, unsigned &ctas, bool two_per_sm = false) {
     const int n_sm = sm_count();
+    static const size_t g_d3 = getenv("TRC_D3_CALLS") ? (size_t)atoi(getenv("TRC_D3_CALLS")) : LPC_MAX_NT / 2;      // A/B runs
     calls_per_cta = LPC_NT / 2;
     const size_t per_sm = (n_calls + n_sm - 1) / n_sm;
+    if (two_per_sm && g_d3 >= 16 && g_d3 <= (size_t)LPC_MAX_NT / 2 && cpc == 0 && per_sm > 3 * (size_t)(LPC_MAX_NT / 2)) {
+        // k_rcs2_dec3, more than one wave, one table: full waves of two equal CTAs per SM (1 GiB at 1760-byte chunks decodes at 636 GB/s
+        // against 433 with 64-call CTAs, whose 34 KB tables keep all but three of them off an SM)
+        const size_t slots = 2 * (size_t)n_sm, waves = (n_calls + slots * g_d3 - 1) / (slots * g_d3);
+        calls_per_cta = (unsigned)((n_calls + slots * waves - 1) / (slots * waves));
+        ctas = (unsigned)((n_calls + calls_per_cta - 1) / calls_per_cta);
+        return;
+    }
     // one wave of equally loaded CTAs: k CTAs per SM (k <= 3 keeps registers and the 33 KB tables of each CTA resident)
     const size_t k = (per_sm + LPC_MAX_NT / 2 - 1) / (LPC_MAX_NT / 2);
     if (cpc == 0 && per_sm > LPC_NT / 2 && k >= 1 && k <= 3) calls_per_cta = (unsigned)((n_calls + (size_t)n_sm * k - 1) / ((size_t)n_sm * k));
     ctas = (unsigned)((n_calls + calls_per_cta - 1) / calls_per_cta);
 }
-// k_rcs2_enc3: ONE CTA per SM (its warps pace each other through shared memory), up to 384 calls = 24 warps each; batches
-// of at most one wave are split evenly over the SMs, bigger ones run in waves of full CTAs
+// k_rcs2_enc3.  A batch of at most 512 calls per SM runs as ONE wave of one CTA per SM (its warps pace each other through shared
+// memory; measured against two half-size CTAs per SM: 601 vs 576 GB/s at 384 calls per SM, 583 vs 558 at 509).  A bigger batch
+// runs as waves of TWO CTAs per SM of at most 256 calls (16 warps: four per scheduler) each, so that one CTA of an SM codes while
+// the other one is in its prologue / layout epilogue: 1 GiB at 1760-byte chunks encodes at 664-669 GB/s against 635 with 384-call
+// CTAs and 582 with 512-call CTAs.  Up to four waves the CTAs are sized equal so that every wave is full (150 MB: 510 vs 481 GB/s).
 static void e3_shape(size_t n_calls, unsigned &calls_per_cta, unsigned &ctas) {
-    const size_t n_sm = (size_t)sm_count(), cap = E3_MAX_NT / 2;
+    static const size_t g_one = getenv("TRC_E3_ONE") ? (size_t)atoi(getenv("TRC_E3_ONE")) : E3_MAX_NT / 2;       // A/B runs
+    static const size_t g_cap = getenv("TRC_E3_CALLS") ? (size_t)atoi(getenv("TRC_E3_CALLS")) : 256;
+    const size_t n_sm = (size_t)sm_count();
     size_t per = (n_calls + n_sm - 1) / n_sm;
-    if (per > cap) per = cap;
+    if (per > (g_one < (size_t)E3_MAX_NT / 2 ? g_one : (size_t)E3_MAX_NT / 2)) {
+        const size_t cap = g_cap < 16 ? 16 : g_cap > E3_MAX_NT / 2 ? E3_MAX_NT / 2 : g_cap, slots = 2 * n_sm;
+        const size_t waves = (n_calls + slots * cap - 1) / (slots * cap);
+        per = cap;
+        if (waves <= 4) { per = (n_calls + slots * waves - 1) / (slots * waves); per = (per + 15) & ~(size_t)15; }   // whole warps
+    }
     if (per < 16) per = 16;
     calls_per_cta = (unsigned)per;
     ctas = (unsigned)((n_calls + per - 1) / per);
@@ -462,7 +481,7 @@ static int dec_batch_impl(int codec, const unsigned char *d_in, const uint64_t *
             g_launches++;
         }
         prof_mark(st);
-        unsigned cpcta, ctas; lpc_shape(g.n_calls, chunks_per_cdf, cpcta, ctas);
+        unsigned cpcta, ctas; lpc_shape(g.n_calls, chunks_per_cdf, cpcta, ctas, true);
         const unsigned nt2 = (2 * cpcta + 31) & ~31u;
         k_rcs2_dec3<<<ctas, nt2, D3_SMEM, st>>>(d_in, d_in_off, d_out, g, g.n_calls, t2, cdfnum, chunks_per_cdf, cpcta);
         g_launches++; prof_mark(st);
