@@ -7,8 +7,12 @@
 #include <cstdlib>
 #include <vector>
 #include <cmath>
+#include <type_traits>
 #include <cuda_runtime.h>
-constexpr int T = 384;
+#ifndef T_LANES
+#define T_LANES 384
+#endif
+constexpr int T = T_LANES;
 static int g_idx = 0;
 constexpr int PROB_BITS = 15;
 constexpr int RING_W = 16;
@@ -129,6 +133,162 @@ struct D3 {
     }
 };
 
+// ---- variant 4: the library's RcD3::step (floor inside the FMA: fma.rm into the 2^23 integer grid)
+struct D4 {
+    uint32_t rl, rh, cl, ch, n0, k; bool bad;
+    const uint8_t *lut; const uint2 *dtab2; uint32_t ringlane;
+    __device__ __forceinline__ void step(uint32_t &x_out) {
+        rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;
+        float qf;
+        asm("fma.rm.f32 %0, %1, %2, 0f4B400000;" : "=f"(qf) : "f"(__ull2float_rz((uint64_t)ch << 32 | cl)), "f"(rcp_approx(__ull2float_rn((uint64_t)rh << 32 | rl))));
+        const uint32_t x = lut[__float_as_uint(qf) & 0x7fffu];
+        const uint2 e = dtab2[x];
+        const uint64_t rp = (uint64_t)rl * e.x, fr = (uint64_t)rl * e.y;
+        const uint32_t pl = (uint32_t)rp, ph = (uint32_t)(rp >> 32) + rh * e.x;
+        const uint32_t fl = (uint32_t)fr, fh = (uint32_t)(fr >> 32) + rh * e.y;
+        uint32_t dl, dh;
+        asm("sub.cc.u32 %0, %2, %4;\n\tsubc.u32 %1, %3, %5;" : "=r"(dl), "=r"(dh) : "r"(cl), "r"(ch), "r"(pl), "r"(ph));
+        bad |= ((uint64_t)dh << 32 | dl) >= ((uint64_t)fh << 32 | fl);
+        uint32_t a;
+        asm("mad.hi.u32 %0, %1, 32768, %2;" : "=r"(a) : "r"(k), "r"(ringlane));
+        asm volatile("{\n\t.reg .pred p;\n\t"
+            "setp.eq.u32 p, %7, 0;\n\t"
+            "selp.u32 %0, %6, %7, p;\n\t"
+            "selp.u32 %1, 0, %6, p;\n\t"
+            "selp.u32 %2, %8, %9, p;\n\t"
+            "selp.u32 %3, %4, %8, p;\n\t"
+            "@p ld.shared.u32 %4, [%10];\n\t"
+            "@p add.u32 %5, %5, 0x10000000;\n\t"
+            "}" : "=r"(rh), "=r"(rl), "=r"(ch), "=r"(cl), "+r"(n0), "+r"(k) : "r"(fl), "r"(fh), "r"(dl), "r"(dh), "r"(a) : "memory");
+        x_out = x;
+    }
+};
+// ---- variant 7: variant 4 with {cdf, freq} packed in ONE 32-bit table entry (LDS.32: half the shared-memory passes of LDS.64, two unpack instructions)
+struct D7 {
+    uint32_t rl, rh, cl, ch, n0, k; bool bad;
+    const uint8_t *lut; const uint32_t *dtab; const uint2 *dtab2; uint32_t ringlane;
+    __device__ __forceinline__ void step(uint32_t &x_out) {
+        rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;
+        float qf;
+        asm("fma.rm.f32 %0, %1, %2, 0f4B400000;" : "=f"(qf) : "f"(__ull2float_rz((uint64_t)ch << 32 | cl)), "f"(rcp_approx(__ull2float_rn((uint64_t)rh << 32 | rl))));
+        const uint32_t x = lut[__float_as_uint(qf) & 0x7fffu];
+        const uint32_t e = dtab[x], ex = e >> 16, ey = e & 0xffffu;
+        const uint64_t rp = (uint64_t)rl * ex, fr = (uint64_t)rl * ey;
+        const uint32_t pl = (uint32_t)rp, ph = (uint32_t)(rp >> 32) + rh * ex;
+        const uint32_t fl = (uint32_t)fr, fh = (uint32_t)(fr >> 32) + rh * ey;
+        uint32_t dl, dh;
+        asm("sub.cc.u32 %0, %2, %4;\n\tsubc.u32 %1, %3, %5;" : "=r"(dl), "=r"(dh) : "r"(cl), "r"(ch), "r"(pl), "r"(ph));
+        bad |= ((uint64_t)dh << 32 | dl) >= ((uint64_t)fh << 32 | fl);
+        uint32_t a;
+        asm("mad.hi.u32 %0, %1, 32768, %2;" : "=r"(a) : "r"(k), "r"(ringlane));
+        asm volatile("{\n\t.reg .pred p;\n\t"
+            "setp.eq.u32 p, %7, 0;\n\t"
+            "selp.u32 %0, %6, %7, p;\n\t"
+            "selp.u32 %1, 0, %6, p;\n\t"
+            "selp.u32 %2, %8, %9, p;\n\t"
+            "selp.u32 %3, %4, %8, p;\n\t"
+            "@p ld.shared.u32 %4, [%10];\n\t"
+            "@p add.u32 %5, %5, 0x10000000;\n\t"
+            "}" : "=r"(rh), "=r"(rl), "=r"(ch), "=r"(cl), "+r"(n0), "+r"(k) : "r"(fl), "r"(fh), "r"(dl), "r"(dh), "r"(a) : "memory");
+        x_out = x;
+    }
+};
+// ---- variant 12: variant 7 with the 32-bit table replicated once per lane (entry of symbol x for lane l at word 32 x + l: always one conflict-free pass)
+struct D12 {
+    uint32_t rl, rh, cl, ch, n0, k; bool bad;
+    const uint8_t *lut; const uint32_t *dtab; const uint2 *dtab2; uint32_t ringlane;
+    __device__ __forceinline__ void step(uint32_t &x_out) {
+        rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;
+        float qf;
+        asm("fma.rm.f32 %0, %1, %2, 0f4B400000;" : "=f"(qf) : "f"(__ull2float_rz((uint64_t)ch << 32 | cl)), "f"(rcp_approx(__ull2float_rn((uint64_t)rh << 32 | rl))));
+        const uint32_t x = lut[__float_as_uint(qf) & 0x7fffu];
+        const uint32_t e = dtab[x * 32], ex = e >> 16, ey = e & 0xffffu;
+        const uint64_t rp = (uint64_t)rl * ex, fr = (uint64_t)rl * ey;
+        const uint32_t pl = (uint32_t)rp, ph = (uint32_t)(rp >> 32) + rh * ex;
+        const uint32_t fl = (uint32_t)fr, fh = (uint32_t)(fr >> 32) + rh * ey;
+        uint32_t dl, dh;
+        asm("sub.cc.u32 %0, %2, %4;\n\tsubc.u32 %1, %3, %5;" : "=r"(dl), "=r"(dh) : "r"(cl), "r"(ch), "r"(pl), "r"(ph));
+        bad |= ((uint64_t)dh << 32 | dl) >= ((uint64_t)fh << 32 | fl);
+        uint32_t a;
+        asm("mad.hi.u32 %0, %1, 32768, %2;" : "=r"(a) : "r"(k), "r"(ringlane));
+        asm volatile("{\n\t.reg .pred p;\n\t"
+            "setp.eq.u32 p, %7, 0;\n\t"
+            "selp.u32 %0, %6, %7, p;\n\t"
+            "selp.u32 %1, 0, %6, p;\n\t"
+            "selp.u32 %2, %8, %9, p;\n\t"
+            "selp.u32 %3, %4, %8, p;\n\t"
+            "@p ld.shared.u32 %4, [%10];\n\t"
+            "@p add.u32 %5, %5, 0x10000000;\n\t"
+            "}" : "=r"(rh), "=r"(rl), "=r"(ch), "=r"(cl), "+r"(n0), "+r"(k) : "r"(fl), "r"(fh), "r"(dl), "r"(dh), "r"(a) : "memory");
+        x_out = x;
+    }
+};
+// ---- variant 5: variant 4 with the renormalisation selects as multiply-adds by a 0/1 word (FMA pipe instead of ALU pipe):
+//      renorm <=> fh == 0, and then dh == 0 too in a valid step, so  rh = fh + pi*fl,  rl = np*fl,  ch = dh + pi*dl,  cl = np*dl + pi*n0
+struct D5 {
+    uint32_t rl, rh, cl, ch, n0, k; bool bad;
+    const uint8_t *lut; const uint2 *dtab2; uint32_t ringlane;
+    __device__ __forceinline__ void step(uint32_t &x_out) {
+        rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;
+        float qf;
+        asm("fma.rm.f32 %0, %1, %2, 0f4B400000;" : "=f"(qf) : "f"(__ull2float_rz((uint64_t)ch << 32 | cl)), "f"(rcp_approx(__ull2float_rn((uint64_t)rh << 32 | rl))));
+        const uint32_t x = lut[__float_as_uint(qf) & 0x7fffu];
+        const uint2 e = dtab2[x];
+        const uint64_t rp = (uint64_t)rl * e.x, fr = (uint64_t)rl * e.y;
+        const uint32_t pl = (uint32_t)rp, ph = (uint32_t)(rp >> 32) + rh * e.x;
+        const uint32_t fl = (uint32_t)fr, fh = (uint32_t)(fr >> 32) + rh * e.y;
+        uint32_t dl, dh;
+        asm("sub.cc.u32 %0, %2, %4;\n\tsubc.u32 %1, %3, %5;" : "=r"(dl), "=r"(dh) : "r"(cl), "r"(ch), "r"(pl), "r"(ph));
+        bad |= ((uint64_t)dh << 32 | dl) >= ((uint64_t)fh << 32 | fl);
+        uint32_t a;
+        asm("mad.hi.u32 %0, %1, 32768, %2;" : "=r"(a) : "r"(k), "r"(ringlane));
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 np, pi, t;\n\t"
+            "setp.eq.u32 p, %7, 0;\n\t"
+            "min.u32 np, %7, 1;\n\t"
+            "mad.lo.u32 pi, np, -1, 1;\n\t"
+            "mad.lo.u32 %0, %6, pi, %7;\n\t"       // rh = fh + pi*fl
+            "mul.lo.u32 %1, %6, np;\n\t"           // rl = np*fl
+            "mad.lo.u32 %2, %8, pi, %9;\n\t"       // ch = dh + pi*dl
+            "mul.lo.u32 t, %8, np;\n\t"
+            "mad.lo.u32 %3, %4, pi, t;\n\t"        // cl = np*dl + pi*n0
+            "@p ld.shared.u32 %4, [%10];\n\t"
+            "mad.lo.u32 %5, pi, 0x10000000, %5;\n\t"
+            "}" : "=r"(rh), "=r"(rl), "=r"(ch), "=r"(cl), "+r"(n0), "+r"(k) : "r"(fl), "r"(fh), "r"(dl), "r"(dh), "r"(a) : "memory");
+        x_out = x;
+    }
+};
+// ---- variant 6: variant 4 with only the two "free" selects moved (rh and ch: one IMAD each, no extra operand) and k by IMAD
+struct D6 {
+    uint32_t rl, rh, cl, ch, n0, k; bool bad;
+    const uint8_t *lut; const uint2 *dtab2; uint32_t ringlane;
+    __device__ __forceinline__ void step(uint32_t &x_out) {
+        rl = __funnelshift_r(rl, rh, PROB_BITS); rh >>= PROB_BITS;
+        float qf;
+        asm("fma.rm.f32 %0, %1, %2, 0f4B400000;" : "=f"(qf) : "f"(__ull2float_rz((uint64_t)ch << 32 | cl)), "f"(rcp_approx(__ull2float_rn((uint64_t)rh << 32 | rl))));
+        const uint32_t x = lut[__float_as_uint(qf) & 0x7fffu];
+        const uint2 e = dtab2[x];
+        const uint64_t rp = (uint64_t)rl * e.x, fr = (uint64_t)rl * e.y;
+        const uint32_t pl = (uint32_t)rp, ph = (uint32_t)(rp >> 32) + rh * e.x;
+        const uint32_t fl = (uint32_t)fr, fh = (uint32_t)(fr >> 32) + rh * e.y;
+        uint32_t dl, dh;
+        asm("sub.cc.u32 %0, %2, %4;\n\tsubc.u32 %1, %3, %5;" : "=r"(dl), "=r"(dh) : "r"(cl), "r"(ch), "r"(pl), "r"(ph));
+        bad |= ((uint64_t)dh << 32 | dl) >= ((uint64_t)fh << 32 | fl);
+        uint32_t a;
+        asm("mad.hi.u32 %0, %1, 32768, %2;" : "=r"(a) : "r"(k), "r"(ringlane));
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .u32 pi;\n\t"
+            "setp.eq.u32 p, %7, 0;\n\t"
+            "selp.u32 pi, 1, 0, p;\n\t"
+            "mad.lo.u32 %0, %6, pi, %7;\n\t"       // rh = fh + pi*fl
+            "selp.u32 %1, 0, %6, p;\n\t"           // rl = p ? 0 : fl
+            "mad.lo.u32 %2, %8, pi, %9;\n\t"       // ch = dh + pi*dl
+            "selp.u32 %3, %4, %8, p;\n\t"          // cl = p ? n0 : dl
+            "@p ld.shared.u32 %4, [%10];\n\t"
+            "mad.lo.u32 %5, pi, 0x10000000, %5;\n\t"
+            "}" : "=r"(rh), "=r"(rl), "=r"(ch), "=r"(cl), "+r"(n0), "+r"(k) : "r"(fl), "r"(fh), "r"(dl), "r"(dh), "r"(a) : "memory");
+        x_out = x;
+    }
+};
+
 template <int V>
 __global__ void __launch_bounds__(T, 2) k(const uint4 *__restrict__ in, const uint32_t *__restrict__ gdtab, const uint8_t *__restrict__ glut,
                                           uint2 *__restrict__ out, uint32_t *__restrict__ flags, int nblk) {
@@ -137,8 +297,11 @@ __global__ void __launch_bounds__(T, 2) k(const uint4 *__restrict__ in, const ui
     uint8_t *lut = dyn + RING_W * 512 * 4;
     uint2 *dtab2 = (uint2 *)(lut + 32768);
     uint32_t *dtab = (uint32_t *)(dtab2 + 256);
+    uint32_t *rep = dtab + 256;                                       // V == 12: 256 symbols x 32 lanes
+    uint8_t *stage = (uint8_t *)(((uintptr_t)(dtab + 256) + 1023) & ~(uintptr_t)1023);   // V == 16: 2 KB per warp
     for (int i = threadIdx.x; i < 256; i += T) { dtab[i] = gdtab[i]; dtab2[i] = make_uint2(gdtab[i] >> 16, gdtab[i] & 0xffff); }
     for (int i = threadIdx.x; i < 32768 / 16; i += T) ((uint4 *)lut)[i] = ((const uint4 *)glut)[i];
+    if (V == 12) for (int i = threadIdx.x; i < 256 * 32; i += T) rep[i] = gdtab[i >> 5];
     __syncthreads();
     const size_t gid = (size_t)blockIdx.x * T + threadIdx.x;
     const uint4 *ip = in + gid * (size_t)(nblk + 4);                // private word stream (4 words per block on average is plenty)
@@ -169,15 +332,15 @@ __global__ void __launch_bounds__(T, 2) k(const uint4 *__restrict__ in, const ui
             acc += d.bad; d.bad = 0;
             op[b] = make_uint2(a0, a1);
         }
-    } else if (V == 3) {
-        D3 d; d.lut = lut; d.dtab2 = dtab2; d.ringlane = (uint32_t)__cvta_generic_to_shared(ring);
+    } else if (V >= 3) {
+        typename std::conditional<V == 3, D3, typename std::conditional<V == 4, D4, typename std::conditional<V == 5, D5, typename std::conditional<V == 6, D6, typename std::conditional<V == 7 || V == 11, D7, typename std::conditional<V == 12, D12, D4>::type>::type>::type>::type>::type>::type d; d.lut = lut; d.dtab2 = dtab2; if constexpr (V == 7 || V == 11) d.dtab = dtab; if constexpr (V == 12) d.dtab = rep + (threadIdx.x & 31); d.ringlane = (uint32_t)__cvta_generic_to_shared(ring);
         d.rl = d.rh = 0xffffffffu; d.ch = ring[0] >> 1; d.cl = ring[RS]; d.n0 = ring[2 * RS]; d.bad = false; d.k = 3u << 28;
         uint32_t ci = 3, k_prev = d.k;
 #pragma unroll 1
         for (int b = 0; b < nblk; b++) {
             const bool need = fi - ci <= 10;
             uint4 t4 = make_uint4(0, 0, 0, 0);
-            if (need) t4 = ip[qi];
+            if (need) t4 = (V == 8 || V == 10) ? in[(size_t)blockIdx.x * T * (nblk + 4) + (size_t)qi * T + threadIdx.x] : ip[qi];   // 8/10: lane-adjacent (coalesced) stream words
             uint32_t a0 = 0, a1 = 0, x;
 #pragma unroll
             for (int s = 0; s < 4; s++) { d.step(x); a0 |= x << (8 * s); }
@@ -186,7 +349,31 @@ __global__ void __launch_bounds__(T, 2) k(const uint4 *__restrict__ in, const ui
             ci += (d.k - k_prev) >> 28; k_prev = d.k;
             if (need) { ring_put(fi, t4); fi += 4; qi++; }
             acc += d.bad ? 1u : 0u; d.bad = false;
-            op[b] = make_uint2(a0, a1);
+            if (V >= 13) {                                                            // the library's geometry: lanes 2r / 2r+1 own bytes [0,8) / [8,16) of every 16-byte block of call r
+                uint2 *cp = out + ((gid >> 1) * (size_t)nblk + b) * 2 + (gid & 1);
+                const uint2 v = make_uint2(a0, a1);
+                if (V == 13) *cp = v;
+                else if (V == 14) __stcs(cp, v);
+                else if (V == 15) asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" :: "l"(cp), "r"(v.x), "r"(v.y) : "memory");
+                else if (V == 16) {                                                   // 8 blocks = 128 bytes per call in a swizzled warp tile, then 4 coalesced 128-bit stores per lane
+                    const uint32_t lane = threadIdx.x & 31, row = lane >> 1;
+                    uint8_t *tile = stage + (threadIdx.x >> 5) * 2048;
+                    *(uint2 *)(tile + row * 128 + ((((uint32_t)b ^ row) & 7) << 4) + 8 * (lane & 1)) = v;
+                    if ((b & 7) == 7) {
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t r2 = q * 4 + (lane >> 3), ch = lane & 7;
+                            const uint4 w = *(const uint4 *)(tile + r2 * 128 + (((ch ^ r2) & 7) << 4));
+                            const size_t call = (((size_t)blockIdx.x * T + (threadIdx.x & ~31u)) >> 1) + r2;
+                            *(uint4 *)((uint8_t *)out + (call * (size_t)nblk + (b & ~7)) * 16 + ch * 16) = w;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            else if (V >= 9) out[((size_t)blockIdx.x * nblk + b) * T + threadIdx.x] = make_uint2(a0, a1);      // 9-12: lane-adjacent (coalesced) output
+            else op[b] = make_uint2(a0, a1);
         }
     } else {
         typename std::conditional<V == 1, D1, D2>::type d;
@@ -220,7 +407,7 @@ static void run(const char *name, const uint4 *d_in, const uint32_t *d_tab, cons
     const int me = g_idx++;
     if (getenv("UB_ONLY") && atoi(getenv("UB_ONLY")) != me) return;
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    const size_t sm = (size_t)RING_W * 512 * 4 + 32768 + 2048 + 1024;
+    const size_t sm = (size_t)RING_W * 512 * 4 + 32768 + 2048 + 1024 + (V == 12 ? 32768 : 0) + (V == 16 ? 1024 + (T / 32) * 2048 : 0);
     cudaFuncSetAttribute(k<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     for (int i = 0; i < 3; i++) k<V><<<ctas, T, sm>>>(d_in, d_tab, d_lut, d_out, d_flags, nblk);
     cudaEventRecord(a);
@@ -259,5 +446,18 @@ int main(int argc, char **argv) {
     run<1>("d1 32-bit cvt, single test, 2-word la", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
     run<3>("d3 64-bit cvt, folded magic, top-bit cursor", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
     run<2>("d2 same, 1-word look-ahead", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<4>("d4 library step (fma.rm)", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<5>("d5 renorm selects as 0/1 IMADs", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<6>("d6 two selects + cursor as IMADs", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<7>("d7 library step, 32-bit table entries", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<8>("d8 = d4, coalesced stream loads", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<9>("d9 = d4, coalesced output stores", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<10>("d10 = d4, both coalesced", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<11>("d11 = d7 (32-bit entries), coalesced stores", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<12>("d12 = lane-replicated 32-bit table, coalesced stores", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<13>("d13 = d4, library output geometry (16 B per call and block)", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<14>("d14 = d13 with st.cs", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<15>("d15 = d13 with L1::no_allocate", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
+    run<16>("d16 = d13 staged: 128 B per call, coalesced STG.128", d_in, d_tab, d_lut, d_out, d_flags, nblk, ctas);
     return 0;
 }
