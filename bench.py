@@ -226,7 +226,7 @@ def run_reference(args):
             "ratio": round(r["clen"] / args.size, 5), "compressed_bytes": int(r["clen"]), "stream_sha16": sha16(stream),
             "cpu_baseline": {"value": round(val, 4), "unit": "GB/s", "cores": threads, "kind": r["kind"], "sample": sample},
             "e2e": {"value": round(val, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -322,8 +322,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):   # NCCL's version banner goes to stdout, where only the JSON line belongs
-            os.environ["NCCL_DEBUG"] = "WARN"
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):     # these two levels print NCCL's version banner (claim_stdout() keeps it off stdout anyway)
+            os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=dev)
     trc = importlib.import_module("turbo-range-coder_b200")
     shard = importlib.import_module("turbo-range-coder_b200.shard")
@@ -632,10 +632,30 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
     if extras:
         line.update(extras)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
     return 0
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON line: keep a private handle on the real stdout and point file descriptor 1 at stderr,
+    so that nothing a library prints (NCCL writes its version banner to stdout with NCCL_DEBUG=VERSION or WARN) can land there."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -657,6 +677,7 @@ def main():
     ap.add_argument("--no-gate", action="store_true", help="skip the oracle comparison of the packed stream (device round trip only)")
     ap.add_argument("--no-extras", action="store_true", help="skip the chunk sweep and the BASELINE config 3/4 lines (extra keys of the JSON line)")
     args = ap.parse_args()
+    claim_stdout()
     if args.quick:
         args.no_gate = args.no_cpu = args.no_extras = args.no_multi_e2e = True
     return run_reference(args) if args.impl == "reference" else run_ours(args)
