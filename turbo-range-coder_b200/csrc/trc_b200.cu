@@ -86,8 +86,8 @@ struct Plan {
 static inline size_t n_tables(size_t n_calls, size_t cpc) { return cpc ? (n_calls + cpc - 1) / cpc : 1; }
 // the throughput kernels (static_v2.cuh) need 16-byte aligned calls and table groups that do not split a CTA
 // lane-per-coder launch shape: (calls per CTA, CTAs).  Batches that fit one wave get one equally loaded CTA per SM.
-static void lpc_shape(size_t n_calls, size_t cpc, unsigned &calls_per_cta, unsigned &ctas, bool two_per_sm = false) {
-    const int n_sm = sm_count();
+static void lpc_shape(size_t n_calls, size_t cpc, unsigned &calls_per_cta, unsigned &ctas, bool two_per_sm = false, int n_sm_in = 0) {
+    const int n_sm = n_sm_in > 0 ? n_sm_in : sm_count();
     static const size_t g_d3 = getenv("TRC_D3_CALLS") ? (size_t)atoi(getenv("TRC_D3_CALLS")) : LPC_MAX_NT / 2;      // A/B runs
     calls_per_cta = LPC_NT / 2;
     const size_t per_sm = (n_calls + n_sm - 1) / n_sm;
@@ -109,10 +109,10 @@ static void lpc_shape(size_t n_calls, size_t cpc, unsigned &calls_per_cta, unsig
 // runs as waves of TWO CTAs per SM of at most 256 calls (16 warps: four per scheduler) each, so that one CTA of an SM codes while
 // the other one is in its prologue / layout epilogue: 1 GiB at 1760-byte chunks encodes at 664-669 GB/s against 635 with 384-call
 // CTAs and 582 with 512-call CTAs.  Up to four waves the CTAs are sized equal so that every wave is full (150 MB: 510 vs 481 GB/s).
-static void e3_shape(size_t n_calls, unsigned &calls_per_cta, unsigned &ctas) {
+static void e3_shape(size_t n_calls, unsigned &calls_per_cta, unsigned &ctas, int n_sm_in = 0) {
     static const size_t g_one = getenv("TRC_E3_ONE") ? (size_t)atoi(getenv("TRC_E3_ONE")) : E3_MAX_NT / 2;       // A/B runs
     static const size_t g_cap = getenv("TRC_E3_CALLS") ? (size_t)atoi(getenv("TRC_E3_CALLS")) : 256;
-    const size_t n_sm = (size_t)sm_count();
+    const size_t n_sm = (size_t)(n_sm_in > 0 ? n_sm_in : sm_count());
     size_t per = (n_calls + n_sm - 1) / n_sm;
     if (per > (g_one < (size_t)E3_MAX_NT / 2 ? g_one : (size_t)E3_MAX_NT / 2)) {
         const size_t cap = g_cap < 16 ? 16 : g_cap > E3_MAX_NT / 2 ? E3_MAX_NT / 2 : g_cap, slots = 2 * n_sm;
@@ -583,6 +583,15 @@ int trc_cdfini_batch_dev(const unsigned char *d_in, size_t total_len, size_t chu
     cudaError_t e = cudaPeekAtLastError();
     cudaFreeAsync(hist, st);
     CK(e);
+    return TRC_OK;
+}
+
+// launch shapes of the TRC_RCS2 kernels for a batch of n_calls calls on a device with n_sm SMs (no device needed: host logic
+// only; tests/test_abi.py checks its invariants).  shape[0..1] = encoder (calls per CTA, CTAs), shape[2..3] = decoder.
+int trc_debug_rcs2_shapes(size_t n_calls, size_t chunks_per_cdf, int n_sm, unsigned shape[4]) {
+    if (!shape || n_sm <= 0 || n_calls == 0) return TRC_E_ARG;
+    e3_shape(n_calls, shape[0], shape[1], n_sm);
+    lpc_shape(n_calls, chunks_per_cdf, shape[2], shape[3], true, n_sm);
     return TRC_OK;
 }
 
