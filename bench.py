@@ -271,13 +271,13 @@ def run_extras(trc, torch, dev, d_zipf, cdf_dev, flush, main_chunk):
     out = {}
     size = d_zipf.numel()
     sweep = []
-    for chunk in sorted({main_chunk, 4096, 65536, 1 << 20}):
+    for chunk in sorted({main_chunk, 4096, 65536, 1 << 20, 4 << 20}):           # {4 KiB, 64 KiB, 1 MiB, 4 MiB}
         b = trc.DeviceBatch(CODECS["rcs2"], size, chunk, cdfnum=256, device=dev)
         b.cdf = cdf_dev
         b.prebuild_tables()
         b.encode(d_zipf); back = b.decode(); torch.cuda.synchronize()
         assert torch.equal(back, d_zipf)
-        e, d = time_batch(trc, torch, b, d_zipf, flush, 3 if chunk >= 65536 else 10)
+        e, d = time_batch(trc, torch, b, d_zipf, flush, 1 if chunk >= (4 << 20) else 3 if chunk >= 65536 else 10)
         sweep.append({"chunk_bytes": chunk, "n_chunks": b.n, "enc_gbs": round(size / e / 1e6, 2), "dec_gbs": round(size / d / 1e6, 2),
                       "value": round(size / (e + d) / 1e6, 2), "ratio": round(b.compressed_len() / size, 5)})
         del b
