@@ -415,3 +415,35 @@ def test_rcs2_extreme_tables(trc, port, dg):
             assert np.array_equal(got, want), (name, chunk, first_diff(got, want))
             back = trc.dec_batch_host(trc.RCS2, got, off, data.size, chunk, cdf=cdf, cdfnum=num)
             assert np.array_equal(back, data), (name, chunk, first_diff(back, data))
+
+
+def test_rcs2_device_shape_boundaries(trc, port, dg):
+    """ONE device batch around the launch-shape boundaries of the TRC_RCS2 kernels (trc_b200.cu e3_shape / lpc_shape: 512 calls
+    per SM = one wave, then waves of two CTAs per SM, balanced up to four waves), with tiny chunks so that the oracle stays fast:
+    packed stream, offsets and round trip, with and without a ragged last call."""
+    import torch
+    from oracle import cpu
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    src = dg.zipf(12_000_000, seed=77)
+    cdf = port.cdfini(src)
+    lib = cpu.ref() or port
+    cases = []
+    for chunk in (16, 48, 128):
+        for calls in (sm * 512 - 1, sm * 512, sm * 512 + 1, sm * 2 * 256 * 2 + 5, sm * 2 * 256 * 4 + 17, sm * 2 * 256 * 5 - 3):
+            for tail in (0, 7):
+                n = calls * chunk + tail
+                if n <= src.size:
+                    cases.append((n, chunk))
+    assert len(cases) >= 12
+    for n, chunk in cases:
+        d = np.ascontiguousarray(src[:n])
+        t = torch.from_numpy(d).cuda()
+        b = trc.DeviceBatch(trc.RCS2, n, chunk, cdfnum=256)
+        b.set_cdf(cdf)
+        b.encode(t); torch.cuda.synchronize()
+        want, woff = cpu.batch_enc(lib, CODECS[trc.RCS2][0], d, chunk, cdf, 256)
+        m = b.compressed_len()
+        assert m == want.size, (n, chunk, m, want.size)
+        assert np.array_equal(b.off.cpu().numpy().view(np.uint64), woff), (n, chunk)
+        assert np.array_equal(b.out[:m].cpu().numpy(), want), (n, chunk)
+        assert torch.equal(b.decode()[:n], t), (n, chunk)
