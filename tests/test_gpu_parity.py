@@ -447,3 +447,35 @@ def test_rcs2_device_shape_boundaries(trc, port, dg):
         assert np.array_equal(b.off.cpu().numpy().view(np.uint64), woff), (n, chunk)
         assert np.array_equal(b.out[:m].cpu().numpy(), want), (n, chunk)
         assert torch.equal(b.decode()[:n], t), (n, chunk)
+
+
+def test_rcs2_fused_per_group_tables(trc, port, dg):
+    """The fused TRC_RCS2 encoder and the round-2 decoder with a table per group of calls (BASELINE config 5's shape), in ONE device
+    batch big enough for the multi-wave launch shapes: groups of 256 calls (256-call CTAs), of 384 (128-call CTAs) and of 128."""
+    import torch
+    from oracle import cpu
+    lib = cpu.ref() or port
+    d = dg.zipf(16 << 20, seed=9)
+    d[5 << 20:9 << 20] = dg.bwt_shaped(4 << 20, seed=10)
+    t = torch.from_numpy(d).cuda()
+    chunk = 128
+    for cpc in (256, 384, 128):
+        b = trc.DeviceBatch(trc.RCS2, d.size, chunk, cdfnum=256, chunks_per_cdf=cpc)
+        b.cdf, status = trc.cdfini_dev(t, d.size, chunk * cpc)
+        assert int(status.abs().sum().item()) == 0
+        nt = -(-b.n // cpc)
+        cdf = b.cdf.cpu().numpy().view(np.uint16).reshape(-1, 257)[:nt]
+        for k in (0, nt // 2, nt - 1):
+            assert np.array_equal(cdf[k], port.cdfini(d[k * chunk * cpc:(k + 1) * chunk * cpc]))
+        want, woff = cpu.batch_enc(lib, CODECS[trc.RCS2][0], d, chunk, cdf, 256, cpc)
+        for pre in (False, True):
+            if pre:
+                b.prebuild_tables()
+            b.out.zero_(); b.off.zero_()
+            b.encode(t); torch.cuda.synchronize()
+            m = b.compressed_len()
+            assert m == want.size, (cpc, pre, m, want.size)
+            assert np.array_equal(b.off.cpu().numpy().view(np.uint64), woff), (cpc, pre)
+            assert np.array_equal(b.out[:m].cpu().numpy(), want), (cpc, pre)
+            assert torch.equal(b.decode()[:d.size], t), (cpc, pre)
+        b.drop_tables()

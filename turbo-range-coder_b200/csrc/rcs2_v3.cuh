@@ -130,7 +130,7 @@ template <bool TMA>
 __global__ void __maxnreg__(64)
 k_rcs2_enc3(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict__ in, Geom g, size_t n_calls,
             const EncTab2 *__restrict__ tab, uint8_t *__restrict__ slots, size_t slot_stride, unsigned calls_per_cta,
-            volatile unsigned long long *__restrict__ lb, uint64_t *__restrict__ out_off, uint8_t *__restrict__ out, unsigned flags) {
+            volatile unsigned long long *__restrict__ lb, uint64_t *__restrict__ out_off, uint8_t *__restrict__ out, unsigned flags, size_t cpc) {
     __shared__ uint64_t bar;
     __shared__ uint64_t fullbar[(E3_MAX_NT / 32) * E3_STAGES];
     __shared__ uint32_t s_len[E3_MAX_NT / 2], s_alen[E3_MAX_NT / 2], s_boff[E3_MAX_NT / 2], s_blen[E3_MAX_NT / 2], s_excl[E3_MAX_NT / 2];
@@ -151,7 +151,7 @@ k_rcs2_enc3(const __grid_constant__ CUtensorMap tmap, const uint8_t *__restrict_
     if (threadIdx.x < 32) s_prog[threadIdx.x] = threadIdx.x < (blockDim.x >> 5) ? 0u : 0xffffffffu;
     if (threadIdx.x == 0) {
         s_tile = (unsigned)atomicAdd((unsigned long long *)(lb + gridDim.x), 1ull);     // tile index in arrival order (look-back safe)
-        tma_fetch(ctab, tab->e, 2048, &bar);
+        tma_fetch(ctab, tab[cpc ? (size_t)s_tile * calls_per_cta / cpc : 0].e, 2048, &bar);   // cpc: calls per table (a CTA never straddles two groups)
         if (TMA) {
             for (unsigned k = 0; k < (blockDim.x >> 5) * E3_STAGES; k++)
                 asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&fullbar[k])));

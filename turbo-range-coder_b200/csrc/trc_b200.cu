@@ -99,6 +99,11 @@ static void lpc_shape(size_t n_calls, size_t cpc, unsigned &calls_per_cta, unsig
         ctas = (unsigned)((n_calls + calls_per_cta - 1) / calls_per_cta);
         return;
     }
+    if (two_per_sm && cpc != 0 && per_sm > 3 * (size_t)(LPC_MAX_NT / 2)) {      // a table per group of calls, more than one wave: the biggest CTA that divides a group
+        calls_per_cta = cpc % 256 == 0 ? 256 : 128;                               // (v2_ok: cpc is a multiple of 128)
+        ctas = (unsigned)((n_calls + calls_per_cta - 1) / calls_per_cta);
+        return;
+    }
     // one wave of equally loaded CTAs: k CTAs per SM (k <= 3 keeps registers and the 33 KB tables of each CTA resident)
     const size_t k = (per_sm + LPC_MAX_NT / 2 - 1) / (LPC_MAX_NT / 2);
     if (cpc == 0 && per_sm > LPC_NT / 2 && k >= 1 && k <= 3) calls_per_cta = (unsigned)((n_calls + (size_t)n_sm * k - 1) / ((size_t)n_sm * k));
@@ -379,14 +384,18 @@ static int enc_batch_impl(int codec, const unsigned char *d_in, size_t total_len
     const bool v2 = codec_static(codec) && v2_ok(d_in, chunk_len, chunks_per_cdf);
     if (codec == ANSW && !(((uintptr_t)d_in & 3) == 0 && (chunks_per_cdf == 0 || chunks_per_cdf % V2_NT == 0))) return TRC_E_ARG;
     TableSet *tabs = pre ? pre->ts : (TableSet *)(sc + p.off_tabs);
-    const bool fused = g_fused && codec == RCS2 && v2 && chunks_per_cdf == 0;
-    if (fused) {                 // TRC_RCS2, one table: coder + offsets + layout in ONE kernel (rcs2_v3.cuh)
+    const bool fused = g_fused && codec == RCS2 && v2;
+    if (fused) {                 // TRC_RCS2: coder + offsets + layout in ONE kernel (rcs2_v3.cuh)
         const size_t n_full = total_len / chunk_len;                        // the tensor map covers full chunks only (see rcs2_v3.cuh)
         EncTab2 *t2 = pre ? pre->e2 : (EncTab2 *)tabs;
         unsigned cpcta = 0, ctas = 0;
         e3_shape(g.n_calls, cpcta, ctas);
+        if (chunks_per_cdf) {                                               // a table per group of calls (v2_ok: a multiple of 128): CTAs of whole groups' divisors
+            cpcta = chunks_per_cdf % 256 == 0 ? 256 : 128;
+            ctas = (unsigned)((g.n_calls + cpcta - 1) / cpcta);
+        }
         CK(cudaMemsetAsync(sc + p.off_lb, 0, (size_t)(ctas + 1) * 8, st));   // look-back words + tile counter
-        if (!pre) { k_build_enctab2<<<1, 256, 0, st>>>(d_cdf, cdfnum, t2); CK_LAUNCH(); }
+        if (!pre) { k_build_enctab2<<<(unsigned)n_tables(g.n_calls, chunks_per_cdf), 256, 0, st>>>(d_cdf, cdfnum, t2); CK_LAUNCH(); }
         prof_mark(st);
         const unsigned nt = (2 * cpcta + 31) & ~31u;
         const bool tma = g_enc_tma && n_full && tmap_encode() && n_full < (1ull << 31);
@@ -401,9 +410,9 @@ static int enc_batch_impl(int codec, const unsigned char *d_in, size_t total_len
         const size_t smem = e3_smem_bytes(nt, tma);
         rc = dev_attrs(); if (rc) return rc;
         if (tma) k_rcs2_enc3<true><<<ctas, nt, smem, st>>>(tm, d_in, g, g.n_calls, t2, slots, p.slot_stride, cpcta,
-                                                          (volatile unsigned long long *)(sc + p.off_lb), d_out_off, d_out, g_force_redo ? 1u : 0u);
+                                                          (volatile unsigned long long *)(sc + p.off_lb), d_out_off, d_out, g_force_redo ? 1u : 0u, chunks_per_cdf);
         else     k_rcs2_enc3<false><<<ctas, nt, smem, st>>>(tm, d_in, g, g.n_calls, t2, slots, p.slot_stride, cpcta,
-                                                           (volatile unsigned long long *)(sc + p.off_lb), d_out_off, d_out, g_force_redo ? 1u : 0u);
+                                                           (volatile unsigned long long *)(sc + p.off_lb), d_out_off, d_out, g_force_redo ? 1u : 0u, chunks_per_cdf);
         CK_LAUNCH();
         prof_mark(st); prof_mark(st); prof_mark(st);
         return TRC_OK;
