@@ -19,6 +19,8 @@
 //    prefetch registers, DRAM sees whole 128-byte lines, and warps never synchronise with each other inside the loop.
 //  * The layout epilogue (decoupled look-back over CTA tiles, copy of the pieces to their final place) is the one of
 //    k_rcs2_enc_fused.
+//  * One table for the batch, or one per aligned group of calls (chunks_per_cdf, a multiple of the CTA's calls): a CTA loads the
+//    table of its group.  Launch shapes (one wave of one CTA per SM / waves of two CTAs per SM): e3_shape, lpc_shape in trc_b200.cu.
 #pragma once
 #include <cuda.h>
 #include "static_v2.cuh"
