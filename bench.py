@@ -509,7 +509,11 @@ def run_ours(args):
     kern_ms = {k: round(v, 4) for k, v in acc.items() if v > 0}
 
     t = torch.tensor([enc_ms, dec_ms, step_ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)                         # per-rank (encode, decode + gather waits, step) ms: who sets the max
+        per_rank = [[round(float(x), 4) for x in a] for a in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     enc_ms, dec_ms, step_ms = float(t[0]), float(t[1]), float(t[2])
     total_bytes = size * world
@@ -628,7 +632,7 @@ def run_ours(args):
             "enc_gbs": round(total_bytes / (enc_ms * 1e-3) / 1e9, 3), "dec_gbs": round(total_bytes / (dec_ms * 1e-3) / 1e9, 3),
             "ratio": round(clen / size, 5), "compressed_bytes": int(clen), "stream_sha16": stream_sha,
             "gate": "whole packed stream + offsets byte-compared with the oracle's at this chunk size" if stream_sha else "device round trip only (--no-gate)",
-            "wall_ms_per_step": round(wall / args.steps * 1e3, 4), "host_enqueue_ms_per_step": round(t_enq / args.steps * 1e3, 4),
+            "per_rank_enc_dec_step_ms": per_rank, "wall_ms_per_step": round(wall / args.steps * 1e3, 4), "host_enqueue_ms_per_step": round(t_enq / args.steps * 1e3, 4),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline}
     if extras:
         line.update(extras)
