@@ -398,7 +398,10 @@ def run_ours(args):
                 # slot sets on rank 0: enough of them that the sources are never held back by acknowledgements while the NVLink
                 # ingress of rank 0 (the bottleneck of an all-to-one gather) is busy; at most ~8 GiB of rank 0's memory
                 depth = int(os.environ.get("TRC_PEER_DEPTH", "0")) or max(2, min(8, (8 << 30) // (world * batch.out.numel())))
-                peer = shard.PeerGather(batch.out.numel(), dst=0, depth=depth)
+                # copy engines per push: one engine moves ~180 GB/s, so up to 4 GPUs (where rank 0's ingress is not the bound) a push is
+                # cut in three -- 4 GPUs: 0.415 -> 0.368 ms per step; beyond that the ingress bound makes it pointless
+                split = int(os.environ.get("TRC_PEER_SPLIT", "0")) or (3 if world <= 4 else 1)
+                peer = shard.PeerGather(batch.out.numel(), dst=0, depth=depth, split=split)
                 ok += 1
             except Exception as e:                      # no peer access
                 print(f"[rank {rank}] PeerGather unavailable ({e})", file=sys.stderr)

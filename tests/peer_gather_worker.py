@@ -30,7 +30,7 @@ def main():
     t = torch.from_numpy(d).to(dev)
     b = trc.DeviceBatch(trc.RCS2, n, chunk, cdfnum=256, device=dev)
     b.set_cdf(cdf)
-    pg = shard.PeerGather(b.out.numel(), dst=0, depth=2)
+    pg = shard.PeerGather(b.out.numel(), dst=0, depth=2, split=3)                  # hinted pushes of >= 1 MiB go out in three pieces
     total_ptr = b.off.data_ptr() + 8 * b.n
     side = torch.cuda.Stream(device=dev)
     for step in range(1, 6):                                 # several rounds through the two slot sets
